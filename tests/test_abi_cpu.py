@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/va_engine.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def va():
+    import vectorizedadjoint_b200 as va
+    if not os.path.exists(va.LIB_PATH):
+        va.build()
+    return va
+
+
+def test_header_symbols_exported(va):
+    hdr = open(os.path.join(ROOT, "include", "va_engine.h")).read()
+    declared = set(re.findall(r"^\s*(?:const\s+)?(?:int|void|char)\s*\*?\s*(va_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert {"va_engine_create", "va_forward_adjoint_batch", "va_forward_batch", "va_adjoint_batch", "va_get_checkpoints",
+            "va_engine_destroy", "va_last_error"} <= declared
+    L = ctypes.CDLL(va.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/va_engine.h but not exported"
+    assert set(va.EXPORTS) == declared
+
+
+def test_struct_layouts_match_header(va):
+    # sizes the C compiler gives the argument structs must equal the ctypes mirrors
+    import subprocess
+    import tempfile
+    src = ('#include "va_engine.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(va_engine_desc), '
+           'sizeof(va_batch_args), sizeof(va_engine_info));return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(va._Desc), ctypes.sizeof(va._Args), ctypes.sizeof(va._Info)]
+
+
+def test_no_cpu_fallback(va):
+    """Without a CUDA device engine creation must fail loudly, never fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(va.EngineError):
+        va.Engine(va.SYS_HARMONIC, 2, va.RK_RK4, False)
+
+
+def test_product_never_touches_oracle():
+    """The product package must not import, link or reference anything under oracle/."""
+    pkg = os.path.join(ROOT, "vectorizedadjoint_b200")
+    for base, _, files in os.walk(pkg):
+        if os.path.basename(base) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "va_oracle.h" not in txt and "libva_ref" not in txt and "import oracle" not in txt, os.path.join(base, f)

@@ -1,0 +1,335 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, libva_engine.so) against the CPU oracle on identical seeded
+inputs, against the committed reference goldens, and through size-independent properties.
+
+Tolerances (BASELINE.json north_star): accepted-step counts equal per trajectory except rounding-induced
+accept/reject flips; final states and adjoint gradients within 1e-8 relative in FP64.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def va():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import vectorizedadjoint_b200 as va
+    va.lib()  # fails loudly when the extension is missing
+    return va
+
+
+def rel_err(a, b, floor=0.0):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b), floor) if floor else np.abs(b).max() if b.size else 1.0
+    return np.abs(a - b).max() / scale if not floor else (np.abs(a - b) / scale).max()
+
+
+def assert_close(a, b, rtol=RTOL, what=""):
+    """max-norm relative agreement per array row (a gradient is judged as a vector, not entry by entry)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    scale = np.abs(b2).max(axis=1, keepdims=True)
+    scale[scale == 0] = 1.0
+    err = (np.abs(a2 - b2) / scale).max()
+    assert err <= rtol, f"{what}: relative error {err:.3e} > {rtol:.1e}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# small systems, thread per trajectory
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_harmonic_golden_and_sweep(va, goldens, synth_goldens):
+    g = goldens["ref17"]["harmonic_rk4"]
+    with va.Engine(va.SYS_HARMONIC, 2, va.RK_RK4, False, max_steps=1024) as e:
+        r = e.forward_adjoint([[0.0, 1.0]], [[0.151]], 0.0, 10.0, 0.01, objective=va.OBJ_HALF_NORM2)
+        assert r["n_accept"][0] == g["steps"] == 1000 and r["status"][0] == 0
+        np.testing.assert_allclose(r["x_final"][0], g["x_final"], rtol=1e-14)
+        np.testing.assert_allclose(r["lam"][0, 0], g["lam"], rtol=1e-12)
+        np.testing.assert_allclose(r["mu"][0, 0], g["mu"], rtol=1e-12)
+        # seeded sweep vs the reference goldens and vs the oracle
+        p = synth_goldens["ho_sweep_params"]
+        r = e.forward_adjoint(oracle.synth_x0(oracle.SYS_HARMONIC, 2, p), p, 0.0, 10.0, 0.01, objective=va.OBJ_HALF_NORM2)
+        np.testing.assert_array_equal(r["n_accept"], synth_goldens["ho_sweep_steps"])
+        np.testing.assert_allclose(r["x_final"], synth_goldens["ho_sweep_x_final"], rtol=1e-13)
+        np.testing.assert_allclose(r["lam"][:, 0], synth_goldens["ho_sweep_lam"], rtol=1e-11)
+        np.testing.assert_allclose(r["mu"][:, 0], synth_goldens["ho_sweep_mu"], rtol=1e-11)
+        o = oracle.forward_adjoint(oracle.SYS_HARMONIC, 2, oracle.RK_RK4, False, 0, 0, oracle.synth_x0(oracle.SYS_HARMONIC, 2, p), p,
+                                   0.0, 10.0, 0.01, objective=oracle.OBJ_HALF_NORM2)
+        # same operation order, no FMA contraction: the forward sweep is bit-identical
+        np.testing.assert_array_equal(r["x_final"], o["x_final"])
+
+
+@pytest.mark.parametrize("tol", ["1e-3", "1e-4", "1e-5", "1e-6", "1e-7", "1e-8", "1e-9", "1e-10", "1e-12"])
+def test_vanderpol_reference_step_counts(va, goldens, tol):
+    """mu = 1e3, RKF78: the nine accepted-step counts printed by the reference binary, and its gradients."""
+    mu0 = 1e3
+    x0 = [2.0, -2.0 / 3.0 + 10.0 / (81.0 * mu0) - 292.0 / (2187.0 * mu0 * mu0)]
+    g = goldens["ref17"][f"vanderpol_rkf78_{tol}"]
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_RKF78, True, float(tol), float(tol), n_out=2, max_steps=2048) as e:
+        r = e.forward_adjoint([x0], [[mu0]], 0.0, 0.5, 1e-3, objective=va.OBJ_SEED, seeds=[[[1, 0], [0, 1]]])
+    assert r["n_accept"][0] == g["steps"] == goldens["printed"]["vanderpol"][tol]["steps"]
+    assert_close(r["x_final"], [g["x_final"]], what="x(tf)")
+    assert_close(r["lam"][0], g["lam"], what="lambda")
+    assert_close(r["mu"][0], g["mu"], what="mu")
+
+
+@pytest.mark.parametrize("stepper,name", [(4, "rkf78"), (2, "ck54"), (3, "dopri5")])
+@pytest.mark.parametrize("tol", [1e-5, 1e-8])
+def test_vanderpol_sweep_vs_oracle(va, stepper, name, tol):
+    B = 512
+    p = oracle.synth_params(oracle.SYS_VANDERPOL, 2, 1234, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_VANDERPOL, 2, p)
+    seeds = np.tile([[1.0, 0.0]], (B, 1))
+    o = oracle.forward_adjoint(oracle.SYS_VANDERPOL, 2, stepper, True, tol, tol, x0, p, 0.0, 0.5, 1e-3, objective=oracle.OBJ_SEED,
+                               seeds=seeds, threads=8)
+    with va.Engine(va.SYS_VANDERPOL, 2, stepper, True, tol, tol, max_steps=2048) as e:
+        r = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+    assert (r["status"] == 0).all()
+    same = r["n_accept"] == o["n_accept"]
+    # pow() on the device is not glibc's: a 1-ulp difference in a step size may flip an accept/reject decision.
+    assert same.mean() >= 0.99, f"{(~same).sum()} of {B} trajectories differ in accepted steps"
+    np.testing.assert_array_equal(r["n_reject"][same], o["n_reject"][same])
+    assert_close(r["x_final"][same], o["x_final"][same], what="x(tf)")
+    assert_close(r["lam"][same, 0], o["lam"][same], what="lambda")
+    assert_close(r["mu"][same, 0], o["mu"][same], what="mu")
+
+
+def test_vanderpol_sweep_vs_reference_goldens(va, synth_goldens):
+    p = synth_goldens["vdp_sweep_params"]
+    B = p.shape[0]
+    x0 = oracle.synth_x0(oracle.SYS_VANDERPOL, 2, p)
+    for name, st in (("rkf78", va.RK_RKF78), ("ck54", va.RK_CK54)):
+        with va.Engine(va.SYS_VANDERPOL, 2, st, True, 1e-8, 1e-8, max_steps=2048) as e:
+            r = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SEED, seeds=np.tile([[1.0, 0.0]], (B, 1)))
+        k = f"vdp_sweep_{name}_1e-8"
+        np.testing.assert_array_equal(r["n_accept"], synth_goldens[k + "_steps"])
+        assert_close(r["x_final"], synth_goldens[k + "_x_final"], what="x(tf)")
+        assert_close(r["lam"][:, 0], synth_goldens[k + "_lam"], what="lambda")
+        assert_close(r["mu"][:, 0], synth_goldens[k + "_mu"], what="mu")
+
+
+def test_scalar_waves_split_api_and_edge_cases(va):
+    B = 1000
+    p = oracle.synth_params(oracle.SYS_VANDERPOL, 2, 99, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_VANDERPOL, 2, p)
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_DOPRI5, True, 1e-6, 1e-6, max_steps=1024) as e:
+        full = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SUM)
+        # reduce = sum equals the sum of the per-trajectory gradients
+        s = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+        np.testing.assert_allclose(s["mu"], full["mu"].sum(axis=0), rtol=1e-12)
+        # split API: forward, checkpoints, adjoint
+        f = e.forward(x0, p, 0.0, 0.5, 1e-3)
+        np.testing.assert_array_equal(f["x_final"], full["x_final"])
+        np.testing.assert_array_equal(f["n_accept"], full["n_accept"])
+        t, x = e.checkpoints(7)
+        assert len(t) == f["n_accept"][7] + 1 and t[0] == 0.0 and abs(t[-1] - 0.5) < 1e-15
+        np.testing.assert_array_equal(x[0], x0[7])
+        np.testing.assert_array_equal(x[-1], f["x_final"][7])
+        assert (np.diff(t) > 0).all()
+        a = e.adjoint(objective=va.OBJ_SUM)
+        np.testing.assert_array_equal(a["lam"], full["lam"])
+        np.testing.assert_array_equal(a["mu"], full["mu"])
+        # empty batch
+        r0 = e.forward_adjoint(np.zeros((0, 2)), np.zeros((0, 1)), 0.0, 0.5, 1e-3)
+        assert r0["x_final"].shape == (0, 2)
+    # a small arena forces several waves; results must not change
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_DOPRI5, True, 1e-6, 1e-6, max_steps=1024, workspace_fraction=1e-6) as e:
+        w = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SUM)
+        assert e.info()["chunk_trajectories"] < B
+        for k in ("x_final", "lam", "mu", "n_accept"):
+            np.testing.assert_array_equal(w[k], full[k])
+    # checkpoint overflow is reported per trajectory, the batch is not aborted
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_DOPRI5, True, 1e-6, 1e-6, max_steps=20) as e:
+        r = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SUM)
+        over = full["n_accept"] > 20
+        assert over.any() and (~over).any()
+        assert ((r["status"] & va.TRAJ_CKPT_OVERFLOW) != 0)[over].all() and (r["status"][~over] == 0).all()
+        np.testing.assert_array_equal(r["mu"][~over], full["mu"][~over])
+        assert np.isnan(r["mu"][over]).all()
+
+
+def test_device_buffers_match_host_buffers(va):
+    import torch
+    B = 4096
+    p = oracle.synth_params(oracle.SYS_VANDERPOL, 2, 5, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_VANDERPOL, 2, p)
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_CK54, True, 1e-6, 1e-6, max_steps=1024) as e:
+        h = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SUM)
+        dev = torch.device("cuda:0")
+        tx0, tp = torch.from_numpy(x0).to(dev), torch.from_numpy(p).to(dev)
+        xf, lam, mu = torch.empty(B, 2, dtype=torch.float64, device=dev), torch.empty(B, 1, 2, dtype=torch.float64, device=dev), \
+            torch.empty(B, 1, 1, dtype=torch.float64, device=dev)
+        na = torch.empty(B, dtype=torch.int32, device=dev)
+        e.call("va_forward_adjoint_batch", B, tx0, tp, 0.0, 0.5, 1e-3, xf, lam, mu, va.OBJ_SUM, va.REDUCE_NONE, na)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(xf.cpu().numpy(), h["x_final"])
+        np.testing.assert_array_equal(lam.cpu().numpy(), h["lam"])
+        np.testing.assert_array_equal(mu.cpu().numpy(), h["mu"])
+        np.testing.assert_array_equal(na.cpu().numpy(), h["n_accept"])
+        # device generator == host generator, bit for bit
+        gp, gx = torch.empty_like(tp), torch.empty_like(tx0)
+        va.synth_batch_device(va.SYS_VANDERPOL, 2, 5, 0, B, gp, gx)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(gp.cpu().numpy(), p)
+        np.testing.assert_array_equal(gx.cpu().numpy(), x0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Generalized Lotka-Volterra, CTA per trajectory
+# ---------------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("N", [5, 10])
+@pytest.mark.parametrize("tol", ["1e-5", "1e-8"])
+def test_glv_reference_example_data(va, goldens, N, tol):
+    """The reference's own parameter files (data/N5, data/N10) through the 64-wide kernel (inert padding species)."""
+    al = np.load(os.path.join(GOLD, f"glv_data_N{N}_alphas.npy"))
+    g = goldens["ref17"][f"glv_N{N}_ck54_{tol}"]
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, float(tol), float(tol)) as e:
+        r = e.forward_adjoint([[0.1] * N], [al], 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+    assert r["status"][0] == 0 and r["n_accept"][0] == g["steps"]
+    assert_close(r["x_final"], [g["x_final"]], what="x(tf)")
+    assert_close(r["lam"][0], [g["lam"]], what="lambda")
+    assert_close(r["mu"][0], [g["mu"]], what="mu")
+
+
+@pytest.mark.parametrize("N,B", [(16, 8), (64, 4)])
+@pytest.mark.parametrize("tol", ["1e-5", "1e-8"])
+def test_glv_synthetic_vs_reference_goldens(va, synth_goldens, N, B, tol):
+    p = oracle.synth_params(oracle.SYS_GLV, N, 1234, 0, B)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, float(tol), float(tol)) as e:
+        r = e.forward_adjoint(oracle.synth_x0(oracle.SYS_GLV, N, p), p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+    k = f"glv_N{N}_ck54_{tol}"
+    np.testing.assert_array_equal(r["n_accept"], synth_goldens[k + "_steps"])
+    assert_close(r["x_final"], synth_goldens[k + "_x_final"], what="x(tf)")
+    assert_close(r["lam"][:, 0], synth_goldens[k + "_lam"], what="lambda")
+    assert_close(r["mu"][:, 0], synth_goldens[k + "_mu"], what="mu")
+
+
+@pytest.mark.parametrize("N,stepper,adaptive,tol,tf,dt0", [
+    (64, 2, True, 1e-8, 10.0, 1e-3), (64, 2, True, 1e-5, 10.0, 1e-3), (64, 3, True, 1e-8, 10.0, 1e-3),
+    (64, 1, False, 0.0, 0.5, 0.01), (16, 2, True, 1e-8, 10.0, 1e-3), (33, 2, True, 1e-6, 10.0, 1e-3), (1, 2, True, 1e-8, 10.0, 1e-3)])
+def test_glv_batch_vs_oracle(va, N, stepper, adaptive, tol, tf, dt0):
+    """More trajectories than resident CTAs: every persistent CTA walks several trajectories."""
+    B = 700 if N == 64 else 300
+    p = oracle.synth_params(oracle.SYS_GLV, N, 4321, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_SUM, threads=8)
+    with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol) as e:
+        r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
+        s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+    assert (r["status"] == 0).all()
+    same = r["n_accept"] == o["n_accept"]
+    assert same.mean() >= 0.99, f"{(~same).sum()} of {B} trajectories differ in accepted steps"
+    np.testing.assert_array_equal(r["n_reject"][same], o["n_reject"][same])
+    assert_close(r["x_final"][same], o["x_final"][same], what="x(tf)")
+    assert_close(r["lam"][same, 0], o["lam"][same], what="lambda")
+    assert_close(r["mu"][same, 0], o["mu"][same], what="mu")
+    # summed-objective mode (per-CTA register accumulation + deterministic reduction) == sum of per-trajectory gradients
+    assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
+    np.testing.assert_array_equal(s["lam"], r["lam"])
+
+
+def test_glv_half_norm_objective_seeds_and_split_api(va):
+    N, B = 64, 37
+    p = oracle.synth_params(oracle.SYS_GLV, N, 77, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0, p, 0.0, 10.0, 1e-3, objective=oracle.OBJ_HALF_NORM2)
+    rng = np.random.default_rng(0)
+    seeds = rng.standard_normal((B, 2, N))
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2)
+        assert_close(r["lam"][:, 0], o["lam"], what="lambda")
+        assert_close(r["mu"][:, 0], o["mu"], what="mu")
+        f = e.forward(x0, p, 0.0, 10.0, 1e-3)
+        np.testing.assert_array_equal(f["x_final"], r["x_final"])
+        t, x = e.checkpoints(B - 1)
+        assert len(t) == f["n_accept"][B - 1] + 1 and t[0] == 0.0 and abs(t[-1] - 10.0) < 1e-14
+        np.testing.assert_array_equal(x[0], x0[B - 1])
+        np.testing.assert_array_equal(x[-1], f["x_final"][B - 1])
+        a = e.adjoint(objective=va.OBJ_HALF_NORM2)
+        np.testing.assert_array_equal(a["mu"], r["mu"])
+    # two explicit seeds per trajectory (the reference's SIMD axis): each must match a single-seed oracle sweep
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=2) as e:
+        r2 = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+        s2 = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+    for k in range(2):
+        ok = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0, p, 0.0, 10.0, 1e-3, objective=oracle.OBJ_SEED,
+                                    seeds=seeds[:, k])
+        assert_close(r2["lam"][:, k], ok["lam"], what=f"lambda seed {k}")
+        assert_close(r2["mu"][:, k], ok["mu"], what=f"mu seed {k}")
+    assert_close(s2["mu"], r2["mu"].sum(axis=0), rtol=1e-11, what="mu sum, 2 seeds")
+
+
+def test_glv_finite_difference_cross_check(va):
+    """Central finite differences of J = sum x_i(tf) w.r.t. a few parameters (fixed-step RK4 so that J is smooth)."""
+    N = 64
+    p = oracle.synth_params(oracle.SYS_GLV, N, 11, 0, 1)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    ks = [0, 17, 63, 64, 64 + 65, 64 + 64 * 10 + 3, 64 + 64 * 63 + 63]
+    h = 1e-6
+    pp = np.repeat(p, 2 * len(ks), axis=0)
+    for m, k in enumerate(ks):
+        pp[2 * m, k] += h
+        pp[2 * m + 1, k] -= h
+    with va.Engine(va.SYS_GLV, N, va.RK_RK4, False, max_steps=256) as e:
+        base = e.forward_adjoint(x0, p, 0.0, 1.0, 0.01, objective=va.OBJ_SUM)
+        pert = e.forward_adjoint(np.repeat(x0, 2 * len(ks), axis=0), pp, 0.0, 1.0, 0.01, objective=va.OBJ_SUM)
+    J = pert["x_final"].sum(axis=1)
+    for m, k in enumerate(ks):
+        fd = (J[2 * m] - J[2 * m + 1]) / (2 * h)
+        assert abs(fd - base["mu"][0, 0, k]) <= 1e-7 * max(abs(fd), 1e-3), (k, fd, base["mu"][0, 0, k])
+
+
+def test_glv_full_size_properties(va):
+    """BASELINE size class (N = 64, tol 1e-8) on device-generated inputs: properties that need no oracle at scale.
+    Linearity of the adjoint in its seed, determinism, step-count statistics, and a sampled oracle comparison."""
+    import torch
+    N, B = 64, 32768
+    npar = N * N + N
+    dev = torch.device("cuda:0")
+    p = torch.empty(B, npar, dtype=torch.float64, device=dev)
+    x0 = torch.empty(B, N, dtype=torch.float64, device=dev)
+    va.synth_batch_device(va.SYS_GLV, N, 1234, 0, B, p, x0)
+    mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
+    xf, lam1, mu1 = mk(B, N), torch.ones(B, 1, N, dtype=torch.float64, device=dev), mk(B, 1, npar)
+    na = torch.empty(B, dtype=torch.int32, device=dev)
+    st = torch.empty(B, dtype=torch.int32, device=dev)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf, lam1, mu1, va.OBJ_SEED, va.REDUCE_NONE, na, None, st)
+        lam3, mu3 = torch.full((B, 1, N), 3.0, dtype=torch.float64, device=dev), mk(B, 1, npar)
+        xf2 = mk(B, N)
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf2, lam3, mu3, va.OBJ_SEED, va.REDUCE_NONE)
+        musum = mk(1, npar)
+        lam_s = torch.ones(B, 1, N, dtype=torch.float64, device=dev)
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf2, lam_s, musum, va.OBJ_SEED, va.REDUCE_SUM)
+        torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0
+    assert torch.equal(xf, xf2)  # deterministic
+    assert torch.isfinite(mu1).all()
+    # the reverse sweep is linear in the seed
+    assert float((mu3 - 3.0 * mu1).abs().max() / mu1.abs().max()) < 1e-13
+    assert float((lam3 - 3.0 * lam1).abs().max() / lam1.abs().max()) < 1e-13
+    # summed objective == sum of per-trajectory gradients
+    ref_sum = mu1[:, 0].sum(dim=0)
+    assert float((musum[0] - ref_sum).abs().max() / ref_sum.abs().max()) < 1e-11
+    steps = na.cpu().numpy()
+    assert 15 <= steps.min() and steps.max() <= 40, (steps.min(), steps.max())
+    # sampled comparison with the oracle on the very same parameter sets (generator is bit-identical host/device)
+    idx = np.array([0, 1, 4095, 12345, B - 1])
+    ph = p[idx].cpu().numpy()
+    np.testing.assert_array_equal(ph, np.concatenate([oracle.synth_params(oracle.SYS_GLV, N, 1234, int(i), 1) for i in idx]))
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0[idx].cpu().numpy(), ph, 0.0, 10.0, 1e-3,
+                               objective=oracle.OBJ_SUM)
+    np.testing.assert_array_equal(steps[idx], o["n_accept"])
+    assert_close(xf[idx].cpu().numpy(), o["x_final"], what="x(tf)")
+    assert_close(mu1[idx, 0].cpu().numpy(), o["mu"], what="mu")
+    assert_close(lam1[idx, 0].cpu().numpy(), o["lam"], what="lambda")

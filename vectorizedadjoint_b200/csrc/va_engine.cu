@@ -1,0 +1,607 @@
+// va_engine.cu -- the C-ABI (include/va_engine.h) on top of the kernel families.
+//
+// Host-side role of the reference's Driver (lib/include/Driver.hpp:15-79): it owns the checkpoint storage
+// (StateStorage -> device arena / slabs), the tableau (ButcherTable -> VaTableau) and the RHS/VJP functors
+// (AadData -> CUDA device functors), and it borrows the caller's lambda / mu buffers for the duration of a call.
+//
+// Memory plan on a 180 GB B200
+//   device-resident calls (mem == VA_MEM_DEVICE): inputs/outputs are the caller's HBM buffers, nothing is staged.
+//     wide GLV family  : one persistent launch over the whole batch; checkpoints in per-CTA slabs (L2-resident).
+//     scalar family    : the batch is cut into arena-sized waves; forward and reverse kernels alternate per wave.
+//   host calls (mem == VA_MEM_HOST): a 3-stream pipeline (H2D | compute | D2H) over double-buffered chunks, so PCIe
+//     transfers of chunk c+1 / c-1 overlap the kernels of chunk c.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "va_common.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define VA_CUDA(call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t err__ = (call);                                                                         \
+        if (err__ != cudaSuccess)                                                                           \
+            return fail(err__ == cudaErrorMemoryAllocation ? VA_E_NOMEM : VA_E_CUDA,                        \
+                        std::string(#call) + ": " + cudaGetErrorString(err__));                             \
+    } while (0)
+
+enum Family { FAM_SCALAR = 0, FAM_GLV_WIDE = 1 };
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return VA_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(VA_E_NOMEM, "cudaMalloc(" + std::to_string(need) + " B) failed"); }
+        bytes = need;
+        return VA_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+} // namespace
+
+struct va_engine {
+    va_engine_desc desc;
+    VaTableau tab;
+    int family = FAM_SCALAR;
+    int device = 0, sm_count = 0;
+    int cap = 0;
+    cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    // wide family
+    int grid = 0, ctas_per_sm = 0, threads = 0;
+    int64_t slab_stride = 0;
+    DevBuf slab, partial;
+    // scalar family
+    DevBuf ck_t, ck_x;
+    int64_t arena_traj = 0;
+    // per-trajectory bookkeeping when the caller passes NULL
+    DevBuf own_accept, own_reject, own_status, mu_tmp;
+    // host-mode staging, two slots
+    DevBuf st_x0[2], st_par[2], st_xf[2], st_lam[2], st_mu[2], st_acc[2], st_rej[2], st_sta[2], st_musum;
+    // split API session (va_forward_batch -> va_adjoint_batch / va_get_checkpoints)
+    DevBuf se_x0, se_par, se_xf, se_lam, se_mu, se_acc, se_rej, se_sta;
+    int64_t se_B = 0;
+    double se_ti = 0, se_tf = 0, se_dt0 = 0;
+    std::vector<int32_t> se_accept_host;
+    std::vector<double> se_xf_host;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    int64_t workspace_bytes = 0, chunk_traj = 0;
+};
+
+namespace {
+
+int64_t per_traj_arena_bytes(const va_engine *e) { return (int64_t)(e->cap + 1) * (e->desc.n_state + 1) * 8; }
+
+int ensure_workspace(va_engine *e, int64_t B)
+{
+    if (e->family == FAM_GLV_WIDE) {
+        const size_t need = (size_t)e->grid * e->slab_stride * 8;
+        if (int rc = e->slab.ensure(need)) return rc;
+        if (int rc = e->partial.ensure((size_t)e->grid * e->desc.n_par * 8)) return rc;
+        e->workspace_bytes = (int64_t)(e->slab.bytes + e->partial.bytes);
+        e->chunk_traj = B;
+        return VA_OK;
+    }
+    // scalar: arena for min(B, budget) trajectories
+    if (e->arena_traj >= B) {
+        e->chunk_traj = B;
+        return VA_OK;
+    }
+    size_t free_b = 0, total_b = 0;
+    VA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double frac = e->desc.workspace_fraction > 0 ? e->desc.workspace_fraction : 0.5;
+    const int64_t have = (int64_t)(e->ck_t.bytes + e->ck_x.bytes);
+    const int64_t budget = (int64_t)(frac * (double)(free_b + have));
+    const int64_t per = per_traj_arena_bytes(e);
+    int64_t traj = std::min<int64_t>(B, std::max<int64_t>(1, budget / per));
+    if (traj < B) traj = std::max<int64_t>(128, traj / 128 * 128); // whole CTAs per wave
+    if (traj > e->arena_traj) {
+        if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * 8)) return rc;
+        if (int rc = e->ck_x.ensure((size_t)traj * (e->cap + 1) * e->desc.n_state * 8)) return rc;
+        e->arena_traj = traj;
+    }
+    e->workspace_bytes = (int64_t)(e->ck_t.bytes + e->ck_x.bytes);
+    e->chunk_traj = std::min<int64_t>(B, e->arena_traj);
+    return VA_OK;
+}
+
+struct DevArgs { // all pointers on the device
+    int64_t B;
+    const double *x0, *params;
+    double ti, tf, dt0;
+    int objective, reduce;
+    double *x_final, *lambda, *mu; // mu: [B][nout][npar] or [nout][npar]
+    int32_t *n_accept, *n_reject, *status;
+    bool mu_accumulate; // VA_REDUCE_SUM: add to mu instead of overwriting (chunked host pipeline)
+    bool forward_only;
+};
+
+// Runs forward (+ adjoint) for device-resident buffers on stream st.
+int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
+{
+    const int n = e->desc.n_state, npar = e->desc.n_par, nout = e->desc.n_out;
+    if (d.B <= 0) return VA_OK;
+    if (int rc = ensure_workspace(e, d.B)) return rc;
+    int32_t *acc = d.n_accept, *rej = d.n_reject, *sta = d.status;
+    if (e->family == FAM_SCALAR) { // the reverse kernel needs them
+        if (!acc) { if (int rc = e->own_accept.ensure((size_t)d.B * 4)) return rc; acc = e->own_accept.as<int32_t>(); }
+        if (!rej) { if (int rc = e->own_reject.ensure((size_t)d.B * 4)) return rc; rej = e->own_reject.as<int32_t>(); }
+        if (!sta) { if (int rc = e->own_status.ensure((size_t)d.B * 4)) return rc; sta = e->own_status.as<int32_t>(); }
+    }
+    const bool sum = d.reduce == VA_REDUCE_SUM;
+
+    if (e->family == FAM_GLV_WIDE) {
+        VaGlvWideArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.n = n; a.stepper = e->desc.stepper; a.adaptive = e->desc.adaptive; a.n_out = d.forward_only ? 0 : nout;
+        a.objective = d.objective;
+        a.eps_abs = e->desc.eps_abs; a.eps_rel = e->desc.eps_rel; a.ti = d.ti; a.tf = d.tf; a.dt0 = d.dt0;
+        a.B = d.B; a.cap = e->cap; a.x0 = d.x0; a.params = d.params; a.x_final = d.x_final; a.lambda = d.lambda;
+        a.n_accept = acc; a.n_reject = rej; a.status = sta;
+        a.slab = e->slab.as<double>(); a.slab_stride = e->slab_stride; a.partial = e->partial.as<double>();
+        a.grid = (int)std::min<int64_t>(e->grid, d.B);
+        const bool native_sum = sum && nout == 1 && !d.forward_only;
+        if (sum && !native_sum && !d.forward_only) {
+            // several cost functions per trajectory: per-trajectory gradients into a scratch buffer, then a row reduction
+            if (int rc = e->mu_tmp.ensure((size_t)d.B * nout * npar * 8)) return rc;
+            a.reduce = VA_REDUCE_NONE;
+            a.mu = e->mu_tmp.as<double>();
+        } else {
+            a.reduce = native_sum ? VA_REDUCE_SUM : VA_REDUCE_NONE;
+            a.mu = d.mu;
+        }
+        VA_CUDA(va_glv_wide_forward_adjoint(a, st));
+        ++e->launches;
+        if (native_sum) {
+            VA_CUDA(va_reduce_rows(e->partial.as<double>(), a.grid, npar, npar, d.mu, d.mu_accumulate ? 1 : 0, st));
+            ++e->launches;
+        } else if (sum && !d.forward_only) {
+            VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), d.B, (int64_t)nout * npar, (int64_t)nout * npar, d.mu,
+                                   d.mu_accumulate ? 1 : 0, st));
+            ++e->launches;
+        }
+        return VA_OK;
+    }
+
+    // scalar family: waves of arena_traj trajectories
+    if (sum && !d.forward_only) {
+        if (int rc = e->mu_tmp.ensure((size_t)std::min<int64_t>(d.B, e->arena_traj) * nout * npar * 8)) return rc;
+    }
+    bool first_wave = true;
+    for (int64_t b0 = 0; b0 < d.B; b0 += e->arena_traj) {
+        const int64_t Bw = std::min<int64_t>(e->arena_traj, d.B - b0);
+        VaScalarArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.system = e->desc.system; a.stepper = e->desc.stepper; a.adaptive = e->desc.adaptive; a.n_out = nout;
+        a.tab = e->tab; a.eps_abs = e->desc.eps_abs; a.eps_rel = e->desc.eps_rel; a.ti = d.ti; a.tf = d.tf; a.dt0 = d.dt0;
+        a.B = Bw; a.arena_stride = e->arena_traj; a.cap = e->cap; a.objective = d.objective;
+        a.x0 = d.x0 + b0 * n; a.params = d.params + b0 * npar; a.x_final = d.x_final + b0 * n;
+        a.lambda = d.lambda ? d.lambda + b0 * nout * n : nullptr;
+        a.mu = sum ? e->mu_tmp.as<double>() : (d.mu ? d.mu + b0 * nout * npar : nullptr);
+        a.n_accept = acc + b0; a.n_reject = rej + b0; a.status = sta + b0;
+        a.ck_t = e->ck_t.as<double>(); a.ck_x = e->ck_x.as<double>();
+        VA_CUDA(va_scalar_forward(a, st));
+        ++e->launches;
+        if (d.forward_only) continue;
+        VA_CUDA(va_scalar_adjoint(a, st));
+        ++e->launches;
+        if (sum) {
+            VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), Bw, (int64_t)nout * npar, (int64_t)nout * npar, d.mu,
+                                   (d.mu_accumulate || !first_wave) ? 1 : 0, st));
+            ++e->launches;
+        }
+        first_wave = false;
+    }
+    return VA_OK;
+}
+
+int check_args(const va_engine *e, const va_batch_args *a, bool need_adjoint)
+{
+    if (!e || !a) return fail(VA_E_INVALID, "null engine or args");
+    if (a->batch < 0) return fail(VA_E_INVALID, "negative batch");
+    if (!a->x0 || !a->params || !a->x_final) return fail(VA_E_INVALID, "x0, params and x_final are required");
+    if (need_adjoint && (!a->lambda || !a->mu)) return fail(VA_E_INVALID, "lambda and mu are required (call setCostGradients first)");
+    if (a->objective < VA_OBJ_SEED || a->objective > VA_OBJ_HALF_NORM2) return fail(VA_E_INVALID, "bad objective");
+    if (a->reduce != VA_REDUCE_NONE && a->reduce != VA_REDUCE_SUM) return fail(VA_E_INVALID, "bad reduce");
+    if (a->mem != VA_MEM_HOST && a->mem != VA_MEM_DEVICE) return fail(VA_E_INVALID, "bad mem");
+    if (a->dt0 == 0.0 || !(std::isfinite(a->ti) && std::isfinite(a->tf) && std::isfinite(a->dt0)))
+        return fail(VA_E_INVALID, "ti, tf, dt0 must be finite and dt0 non-zero");
+    return VA_OK;
+}
+
+// Host buffers: chunked 3-stream pipeline.
+int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
+{
+    const int n = e->desc.n_state, npar = e->desc.n_par, nout = e->desc.n_out;
+    const int64_t B = a->batch;
+    const bool sum = a->reduce == VA_REDUCE_SUM;
+    const int64_t in_bytes = 8LL * (n + npar) + (a->objective == VA_OBJ_SEED ? 8LL * nout * n : 0);
+    const int64_t out_bytes = 8LL * n + 8LL * nout * n + (sum ? 0 : 8LL * nout * npar) + 12;
+    const int64_t slot_budget = 2LL << 30;
+    int64_t Bc = std::max<int64_t>(1, slot_budget / (in_bytes + out_bytes));
+    if (e->family == FAM_GLV_WIDE && Bc > e->grid) Bc = Bc / e->grid * e->grid; // whole waves of CTAs
+    Bc = std::min(Bc, B);
+    if (B == 0) return VA_OK;
+    for (int s = 0; s < 2; ++s) {
+        if (int rc = e->st_x0[s].ensure((size_t)Bc * n * 8)) return rc;
+        if (int rc = e->st_par[s].ensure((size_t)Bc * npar * 8)) return rc;
+        if (int rc = e->st_xf[s].ensure((size_t)Bc * n * 8)) return rc;
+        if (int rc = e->st_lam[s].ensure((size_t)Bc * nout * n * 8)) return rc;
+        if (!sum && !forward_only)
+            if (int rc = e->st_mu[s].ensure((size_t)Bc * nout * npar * 8)) return rc;
+        if (int rc = e->st_acc[s].ensure((size_t)Bc * 4)) return rc;
+        if (int rc = e->st_rej[s].ensure((size_t)Bc * 4)) return rc;
+        if (int rc = e->st_sta[s].ensure((size_t)Bc * 4)) return rc;
+    }
+    if (sum && !forward_only) {
+        if (int rc = e->st_musum.ensure((size_t)nout * npar * 8)) return rc;
+        VA_CUDA(cudaMemsetAsync(e->st_musum.p, 0, (size_t)nout * npar * 8, e->s_comp));
+    }
+    VA_CUDA(cudaEventRecord(e->ev_t0, e->s_comp));
+    int64_t c = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc, ++c) {
+        const int s = (int)(c & 1);
+        const int64_t Bn = std::min(Bc, B - b0);
+        // inputs of this slot are free once the kernels of chunk c-2 are done
+        if (c >= 2) VA_CUDA(cudaStreamWaitEvent(e->s_in, e->ev_comp[s], 0));
+        VA_CUDA(cudaMemcpyAsync(e->st_x0[s].p, a->x0 + b0 * n, (size_t)Bn * n * 8, cudaMemcpyHostToDevice, e->s_in));
+        VA_CUDA(cudaMemcpyAsync(e->st_par[s].p, a->params + b0 * npar, (size_t)Bn * npar * 8, cudaMemcpyHostToDevice, e->s_in));
+        if (!forward_only && a->objective == VA_OBJ_SEED)
+            VA_CUDA(cudaMemcpyAsync(e->st_lam[s].p, a->lambda + b0 * nout * n, (size_t)Bn * nout * n * 8, cudaMemcpyHostToDevice, e->s_in));
+        VA_CUDA(cudaEventRecord(e->ev_in[s], e->s_in));
+        // compute: needs the inputs, and the outputs of this slot drained (chunk c-2)
+        VA_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev_in[s], 0));
+        if (c >= 2) VA_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev_out[s], 0));
+        DevArgs d;
+        d.B = Bn; d.x0 = e->st_x0[s].as<double>(); d.params = e->st_par[s].as<double>();
+        d.ti = a->ti; d.tf = a->tf; d.dt0 = a->dt0; d.objective = a->objective; d.reduce = a->reduce;
+        d.x_final = e->st_xf[s].as<double>(); d.lambda = e->st_lam[s].as<double>();
+        d.mu = sum ? e->st_musum.as<double>() : e->st_mu[s].as<double>();
+        d.n_accept = e->st_acc[s].as<int32_t>(); d.n_reject = e->st_rej[s].as<int32_t>(); d.status = e->st_sta[s].as<int32_t>();
+        d.mu_accumulate = true; d.forward_only = forward_only;
+        if (int rc = run_device(e, d, e->s_comp)) return rc;
+        VA_CUDA(cudaEventRecord(e->ev_comp[s], e->s_comp));
+        // outputs
+        VA_CUDA(cudaStreamWaitEvent(e->s_out, e->ev_comp[s], 0));
+        VA_CUDA(cudaMemcpyAsync(a->x_final + b0 * n, e->st_xf[s].p, (size_t)Bn * n * 8, cudaMemcpyDeviceToHost, e->s_out));
+        if (!forward_only) {
+            VA_CUDA(cudaMemcpyAsync(a->lambda + b0 * nout * n, e->st_lam[s].p, (size_t)Bn * nout * n * 8, cudaMemcpyDeviceToHost, e->s_out));
+            if (!sum)
+                VA_CUDA(cudaMemcpyAsync(a->mu + b0 * nout * npar, e->st_mu[s].p, (size_t)Bn * nout * npar * 8, cudaMemcpyDeviceToHost, e->s_out));
+        }
+        if (a->n_accept) VA_CUDA(cudaMemcpyAsync(a->n_accept + b0, e->st_acc[s].p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, e->s_out));
+        if (a->n_reject) VA_CUDA(cudaMemcpyAsync(a->n_reject + b0, e->st_rej[s].p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, e->s_out));
+        if (a->status) VA_CUDA(cudaMemcpyAsync(a->status + b0, e->st_sta[s].p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, e->s_out));
+        VA_CUDA(cudaEventRecord(e->ev_out[s], e->s_out));
+    }
+    VA_CUDA(cudaEventRecord(e->ev_t1, e->s_comp));
+    if (sum && !forward_only)
+        VA_CUDA(cudaMemcpyAsync(a->mu, e->st_musum.p, (size_t)nout * npar * 8, cudaMemcpyDeviceToHost, e->s_comp));
+    VA_CUDA(cudaStreamSynchronize(e->s_in));
+    VA_CUDA(cudaStreamSynchronize(e->s_comp));
+    VA_CUDA(cudaStreamSynchronize(e->s_out));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
+    e->last_ms = ms;
+    e->chunk_traj = Bc;
+    return VA_OK;
+}
+
+int run_call(va_engine *e, const va_batch_args *a, bool forward_only)
+{
+    VA_CUDA(cudaSetDevice(e->device));
+    if (a->mem == VA_MEM_HOST) return run_host(e, a, forward_only);
+    cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : e->s_comp;
+    DevArgs d;
+    d.B = a->batch; d.x0 = a->x0; d.params = a->params; d.ti = a->ti; d.tf = a->tf; d.dt0 = a->dt0;
+    d.objective = a->objective; d.reduce = a->reduce; d.x_final = a->x_final; d.lambda = a->lambda; d.mu = a->mu;
+    d.n_accept = a->n_accept; d.n_reject = a->n_reject; d.status = a->status; d.mu_accumulate = false;
+    d.forward_only = forward_only;
+    VA_CUDA(cudaEventRecord(e->ev_t0, st));
+    if (int rc = run_device(e, d, st)) return rc;
+    VA_CUDA(cudaEventRecord(e->ev_t1, st));
+    if (!a->stream) {
+        VA_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
+        e->last_ms = ms;
+    }
+    return VA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *va_last_error(void) { return g_last_error.c_str(); }
+
+int va_engine_create(const va_engine_desc *desc, va_engine **out)
+{
+    if (!desc || !out) return fail(VA_E_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->n_state < 1 || desc->n_par < 1 || desc->n_out < 1) return fail(VA_E_INVALID, "n_state, n_par, n_out must be >= 1");
+    VaTableau tab;
+    if (va_tableau_host(desc->stepper, &tab) != 0)
+        return fail(VA_E_UNSUPPORTED, "This stepper is not supported yet!"); // ButcherTable.hpp:121-124, 247-250 (no terminate here)
+    if (desc->adaptive && !tab.has_error)
+        return fail(VA_E_INVALID, "a controlled stepper needs an error stepper (cash_karp54, dopri5, fehlberg78)");
+    if (desc->adaptive && !(desc->eps_abs >= 0 && desc->eps_rel >= 0 && desc->eps_abs + desc->eps_rel > 0))
+        return fail(VA_E_INVALID, "tolerances must be non-negative and not both zero");
+    int family;
+    switch (desc->system) {
+    case VA_SYS_HARMONIC:
+    case VA_SYS_VANDERPOL:
+        if (desc->n_state != 2 || desc->n_par != 1) return fail(VA_E_INVALID, "harmonic / van der pol: n_state = 2, n_par = 1");
+        family = FAM_SCALAR;
+        break;
+    case VA_SYS_GLV:
+        if (desc->n_par != desc->n_state * desc->n_state + desc->n_state) return fail(VA_E_INVALID, "GLV: n_par must be N*N + N");
+        if (!va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive))
+            return fail(VA_E_UNSUPPORTED, "GLV: supported are N <= 64 with rk4 (fixed step), cash_karp54 or dopri5 (controlled)");
+        family = FAM_GLV_WIDE;
+        break;
+    default:
+        return fail(VA_E_UNSUPPORTED, "system kind not available in this build");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VA_E_CUDA, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (desc->device < 0 || desc->device >= ndev) return fail(VA_E_INVALID, "bad device ordinal");
+    va_engine *e = new (std::nothrow) va_engine();
+    if (!e) return fail(VA_E_NOMEM, "out of host memory");
+    e->desc = *desc;
+    e->tab = tab;
+    e->family = family;
+    e->device = desc->device;
+    e->cap = desc->max_steps > 0 ? desc->max_steps : (family == FAM_GLV_WIDE ? 256 : 2048);
+    auto bail = [&](int code, const std::string &m) { va_engine_destroy(e); return fail(code, m); };
+    if (cudaSetDevice(e->device) != cudaSuccess) return bail(VA_E_CUDA, "cudaSetDevice failed");
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device);
+    bool ok = cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&e->ev_t0) == cudaSuccess && cudaEventCreate(&e->ev_t1) == cudaSuccess;
+    for (int s = 0; s < 2 && ok; ++s)
+        ok = cudaEventCreateWithFlags(&e->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->ev_comp[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return bail(VA_E_CUDA, "stream/event creation failed");
+    if (family == FAM_GLV_WIDE) {
+        cudaError_t ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads);
+        if (ce != cudaSuccess) return bail(VA_E_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(ce));
+        e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
+        e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
+    } else {
+        e->threads = 128;
+        e->desc.ckpt_policy = VA_CKPT_RECOMPUTE;
+    }
+    *out = e;
+    return VA_OK;
+}
+
+void va_engine_destroy(va_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    DevBuf *bufs[] = {&e->slab, &e->partial, &e->ck_t, &e->ck_x, &e->own_accept, &e->own_reject, &e->own_status, &e->mu_tmp,
+                      &e->st_musum, &e->se_x0, &e->se_par, &e->se_xf, &e->se_lam, &e->se_mu, &e->se_acc, &e->se_rej, &e->se_sta};
+    for (DevBuf *b : bufs) b->release();
+    for (int s = 0; s < 2; ++s) {
+        DevBuf *sb[] = {&e->st_x0[s], &e->st_par[s], &e->st_xf[s], &e->st_lam[s], &e->st_mu[s], &e->st_acc[s], &e->st_rej[s], &e->st_sta[s]};
+        for (DevBuf *b : sb) b->release();
+        if (e->ev_in[s]) cudaEventDestroy(e->ev_in[s]);
+        if (e->ev_comp[s]) cudaEventDestroy(e->ev_comp[s]);
+        if (e->ev_out[s]) cudaEventDestroy(e->ev_out[s]);
+    }
+    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+    if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+    delete e;
+}
+
+int va_engine_get_info(va_engine *e, va_engine_info *info)
+{
+    if (!e || !info) return fail(VA_E_INVALID, "null argument");
+    std::memset(info, 0, sizeof(*info));
+    info->api_version = VA_API_VERSION;
+    info->device = e->device;
+    info->sm_count = e->sm_count;
+    info->kernel_family = e->family;
+    info->ckpt_policy = e->desc.ckpt_policy;
+    info->max_steps = e->cap;
+    info->ctas_per_sm = e->ctas_per_sm;
+    info->threads_per_cta = e->threads;
+    info->workspace_bytes = e->workspace_bytes;
+    info->chunk_trajectories = e->chunk_traj;
+    info->kernel_launches = e->launches;
+    info->last_kernel_ms = e->last_ms;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) std::snprintf(info->device_name, sizeof(info->device_name), "%s", prop.name);
+    return VA_OK;
+}
+
+int va_forward_adjoint_batch(va_engine *e, const va_batch_args *a)
+{
+    if (int rc = check_args(e, a, true)) return rc;
+    return run_call(e, a, false);
+}
+
+// Split API. The forward call keeps a device-side session (inputs, x(tf), step counts, checkpoints) so that
+// va_adjoint_batch / va_get_checkpoints can serve Driver::GetT/GetTime/GetState and adjointSolve afterwards.
+int va_forward_batch(va_engine *e, const va_batch_args *a)
+{
+    if (int rc = check_args(e, a, false)) return rc;
+    VA_CUDA(cudaSetDevice(e->device));
+    const int n = e->desc.n_state, npar = e->desc.n_par;
+    const int64_t B = a->batch;
+    if (e->family == FAM_GLV_WIDE && B > e->grid)
+        return fail(VA_E_UNSUPPORTED, "split forward/adjoint on the GLV path keeps checkpoints for at most one wave of CTAs; "
+                                      "use va_forward_adjoint_batch for larger batches");
+    if (int rc = e->se_x0.ensure((size_t)B * n * 8)) return rc;
+    if (int rc = e->se_par.ensure((size_t)B * npar * 8)) return rc;
+    if (int rc = e->se_xf.ensure((size_t)B * n * 8)) return rc;
+    if (int rc = e->se_acc.ensure((size_t)B * 4)) return rc;
+    if (int rc = e->se_rej.ensure((size_t)B * 4)) return rc;
+    if (int rc = e->se_sta.ensure((size_t)B * 4)) return rc;
+    const cudaMemcpyKind in_kind = a->mem == VA_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind out_kind = a->mem == VA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    VA_CUDA(cudaMemcpyAsync(e->se_x0.p, a->x0, (size_t)B * n * 8, in_kind, e->s_comp));
+    VA_CUDA(cudaMemcpyAsync(e->se_par.p, a->params, (size_t)B * npar * 8, in_kind, e->s_comp));
+    if (e->family == FAM_SCALAR) {
+        if (int rc = ensure_workspace(e, B)) return rc;
+        if (e->arena_traj < B) return fail(VA_E_NOMEM, "checkpoint arena too small for a split forward/adjoint of this batch; use va_forward_adjoint_batch");
+    }
+    DevArgs d;
+    d.B = B; d.x0 = e->se_x0.as<double>(); d.params = e->se_par.as<double>(); d.ti = a->ti; d.tf = a->tf; d.dt0 = a->dt0;
+    d.objective = VA_OBJ_SUM; d.reduce = VA_REDUCE_NONE; d.x_final = e->se_xf.as<double>(); d.lambda = nullptr; d.mu = nullptr;
+    d.n_accept = e->se_acc.as<int32_t>(); d.n_reject = e->se_rej.as<int32_t>(); d.status = e->se_sta.as<int32_t>();
+    d.mu_accumulate = false; d.forward_only = true;
+    VA_CUDA(cudaEventRecord(e->ev_t0, e->s_comp));
+    if (int rc = run_device(e, d, e->s_comp)) return rc;
+    VA_CUDA(cudaEventRecord(e->ev_t1, e->s_comp));
+    VA_CUDA(cudaMemcpyAsync(a->x_final, e->se_xf.p, (size_t)B * n * 8, out_kind, e->s_comp));
+    if (a->n_accept) VA_CUDA(cudaMemcpyAsync(a->n_accept, e->se_acc.p, (size_t)B * 4, out_kind, e->s_comp));
+    if (a->n_reject) VA_CUDA(cudaMemcpyAsync(a->n_reject, e->se_rej.p, (size_t)B * 4, out_kind, e->s_comp));
+    if (a->status) VA_CUDA(cudaMemcpyAsync(a->status, e->se_sta.p, (size_t)B * 4, out_kind, e->s_comp));
+    e->se_accept_host.resize((size_t)B);
+    e->se_xf_host.resize((size_t)B * n);
+    VA_CUDA(cudaMemcpyAsync(e->se_accept_host.data(), e->se_acc.p, (size_t)B * 4, cudaMemcpyDeviceToHost, e->s_comp));
+    VA_CUDA(cudaMemcpyAsync(e->se_xf_host.data(), e->se_xf.p, (size_t)B * n * 8, cudaMemcpyDeviceToHost, e->s_comp));
+    VA_CUDA(cudaStreamSynchronize(e->s_comp));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
+    e->last_ms = ms;
+    e->se_B = B; e->se_ti = a->ti; e->se_tf = a->tf; e->se_dt0 = a->dt0;
+    return VA_OK;
+}
+
+int va_adjoint_batch(va_engine *e, const va_batch_args *a)
+{
+    if (!e || !a) return fail(VA_E_INVALID, "null engine or args");
+    if (e->se_B <= 0) return fail(VA_E_STATE, "va_adjoint_batch needs a preceding va_forward_batch (runge_kutta) on this engine");
+    if (a->batch != e->se_B) return fail(VA_E_INVALID, "batch differs from the preceding va_forward_batch");
+    if (!a->lambda || !a->mu) return fail(VA_E_INVALID, "Must call setCostGradients() first!"); // backpropagation.hpp:22-26
+    if (a->reduce != VA_REDUCE_NONE && a->reduce != VA_REDUCE_SUM) return fail(VA_E_INVALID, "bad reduce");
+    VA_CUDA(cudaSetDevice(e->device));
+    const int n = e->desc.n_state, npar = e->desc.n_par, nout = e->desc.n_out;
+    const int64_t B = e->se_B;
+    const bool sum = a->reduce == VA_REDUCE_SUM;
+    const size_t mu_elems = sum ? (size_t)nout * npar : (size_t)B * nout * npar;
+    if (int rc = e->se_lam.ensure((size_t)B * nout * n * 8)) return rc;
+    if (int rc = e->se_mu.ensure(mu_elems * 8)) return rc;
+    const cudaMemcpyKind in_kind = a->mem == VA_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind out_kind = a->mem == VA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (a->objective == VA_OBJ_SEED)
+        VA_CUDA(cudaMemcpyAsync(e->se_lam.p, a->lambda, (size_t)B * nout * n * 8, in_kind, e->s_comp));
+    VA_CUDA(cudaEventRecord(e->ev_t0, e->s_comp));
+    if (e->family == FAM_SCALAR) {
+        // reverse kernel over the checkpoints of the session
+        VaScalarArgs s;
+        std::memset(&s, 0, sizeof(s));
+        s.system = e->desc.system; s.stepper = e->desc.stepper; s.adaptive = e->desc.adaptive; s.n_out = nout; s.tab = e->tab;
+        s.B = B; s.arena_stride = e->arena_traj; s.cap = e->cap; s.objective = a->objective;
+        s.params = e->se_par.as<double>(); s.x_final = e->se_xf.as<double>(); s.lambda = e->se_lam.as<double>();
+        s.n_accept = e->se_acc.as<int32_t>(); s.n_reject = e->se_rej.as<int32_t>(); s.status = e->se_sta.as<int32_t>();
+        s.ck_t = e->ck_t.as<double>(); s.ck_x = e->ck_x.as<double>();
+        if (sum) {
+            if (int rc = e->mu_tmp.ensure((size_t)B * nout * npar * 8)) return rc;
+            s.mu = e->mu_tmp.as<double>();
+        } else {
+            s.mu = e->se_mu.as<double>();
+        }
+        VA_CUDA(va_scalar_adjoint(s, e->s_comp));
+        ++e->launches;
+        if (sum) {
+            VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), B, (int64_t)nout * npar, (int64_t)nout * npar, e->se_mu.as<double>(), 0, e->s_comp));
+            ++e->launches;
+        }
+    } else {
+        // GLV path: the fused kernel re-integrates (deterministic, identical checkpoints) and sweeps back
+        DevArgs d;
+        d.B = B; d.x0 = e->se_x0.as<double>(); d.params = e->se_par.as<double>(); d.ti = e->se_ti; d.tf = e->se_tf; d.dt0 = e->se_dt0;
+        d.objective = a->objective; d.reduce = a->reduce; d.x_final = e->se_xf.as<double>(); d.lambda = e->se_lam.as<double>();
+        d.mu = e->se_mu.as<double>(); d.n_accept = e->se_acc.as<int32_t>(); d.n_reject = e->se_rej.as<int32_t>();
+        d.status = e->se_sta.as<int32_t>(); d.mu_accumulate = false; d.forward_only = false;
+        if (int rc = run_device(e, d, e->s_comp)) return rc;
+    }
+    VA_CUDA(cudaEventRecord(e->ev_t1, e->s_comp));
+    VA_CUDA(cudaMemcpyAsync(a->lambda, e->se_lam.p, (size_t)B * nout * n * 8, out_kind, e->s_comp));
+    VA_CUDA(cudaMemcpyAsync(a->mu, e->se_mu.p, mu_elems * 8, out_kind, e->s_comp));
+    VA_CUDA(cudaStreamSynchronize(e->s_comp));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
+    e->last_ms = ms;
+    return VA_OK;
+}
+
+int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, double *x, int32_t *count)
+{
+    if (!e || !count) return fail(VA_E_INVALID, "null argument");
+    if (e->se_B <= 0) return fail(VA_E_STATE, "no forward sweep recorded on this engine");
+    if (b < 0 || b >= e->se_B) return fail(VA_E_INVALID, "trajectory index out of range");
+    const int n = e->desc.n_state;
+    const int T = e->se_accept_host[(size_t)b];
+    *count = T + 1;
+    if (!t && !x) return VA_OK;
+    if (capacity < T + 1) return fail(VA_E_INVALID, "capacity too small");
+    VA_CUDA(cudaSetDevice(e->device));
+    if (e->family == FAM_SCALAR) {
+        const size_t pitch = (size_t)e->arena_traj * 8;
+        if (t) VA_CUDA(cudaMemcpy2D(t, 8, e->ck_t.as<double>() + b, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
+        if (x) VA_CUDA(cudaMemcpy2D(x, 8, e->ck_x.as<double>() + b, pitch, 8, (size_t)(T + 1) * n, cudaMemcpyDeviceToHost));
+    } else {
+        // slab of CTA b: times, then stage-0 states (= x_n) of every accepted step; x_T is x(tf)
+        const double *base = e->slab.as<double>() + b * e->slab_stride;
+        const int tt_len = (e->cap + 2 + 15) & ~15;
+        const int sadj = e->tab.s_adj;
+        if (t) VA_CUDA(cudaMemcpy(t, base, (size_t)(T + 1) * 8, cudaMemcpyDeviceToHost));
+        if (x) {
+            if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + tt_len, (size_t)sadj * 64 * 8, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));
+            std::memcpy(x + (size_t)T * n, e->se_xf_host.data() + (size_t)b * n, (size_t)n * 8);
+        }
+    }
+    return VA_OK;
+}
+
+int va_synth_batch_device(int32_t system, int32_t n_state, uint64_t seed, int64_t b0, int64_t B, double *params_dev, double *x0_dev,
+                          void *stream)
+{
+    if (!params_dev || B < 0) return fail(VA_E_INVALID, "bad argument");
+    VA_CUDA(va_synth_launch(system, n_state, seed, b0, B, params_dev, x0_dev, static_cast<cudaStream_t>(stream)));
+    return VA_OK;
+}
+
+} // extern "C"
