@@ -311,7 +311,6 @@ int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
     e->last_ms = ms;
-    e->chunk_traj = Bc;
     return VA_OK;
 }
 
