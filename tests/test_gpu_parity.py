@@ -286,7 +286,7 @@ def test_glv_finite_difference_cross_check(va):
     J = pert["x_final"].sum(axis=1)
     for m, k in enumerate(ks):
         fd = (J[2 * m] - J[2 * m + 1]) / (2 * h)
-        assert abs(fd - base["mu"][0, 0, k]) <= 1e-7 * max(abs(fd), 1e-3), (k, fd, base["mu"][0, 0, k])
+        assert abs(fd - base["mu"][0, 0, k]) <= 1e-7 * abs(fd) + 5e-9, (k, fd, base["mu"][0, 0, k])  # FD noise ~ eps/h
 
 
 def test_glv_full_size_properties(va):

@@ -71,11 +71,13 @@ struct VaGlvWideArgs {
     int32_t *n_accept, *n_reject, *status;
     double *slab;         // grid * slab_stride doubles
     int64_t slab_stride;
-    double *partial;      // VA_REDUCE_SUM: [grid][n_par] per-CTA partial sums (reduced by va_reduce_partials)
+    double *partial;      // VA_REDUCE_SUM: [grid][n_par] per-CTA partial sums (reduced by va_reduce_rows)
     int grid;
+    struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);
+int va_glv_wide_block_doubles(int stepper); // step block: [8-double header (t_n) | X_0..X_{s-1} | g_0..g_{s-1}], 64 wide
 cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads);
 cudaError_t va_glv_wide_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 

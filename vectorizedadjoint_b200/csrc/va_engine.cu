@@ -582,13 +582,13 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, e->ck_t.as<double>() + b, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) VA_CUDA(cudaMemcpy2D(x, 8, e->ck_x.as<double>() + b, pitch, 8, (size_t)(T + 1) * n, cudaMemcpyDeviceToHost));
     } else {
-        // slab of CTA b: times, then stage-0 states (= x_n) of every accepted step; x_T is x(tf)
+        // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
+        // carries the final time only; x_T is x(tf).
         const double *base = e->slab.as<double>() + b * e->slab_stride;
-        const int tt_len = (e->cap + 2 + 15) & ~15;
-        const int sadj = e->tab.s_adj;
-        if (t) VA_CUDA(cudaMemcpy(t, base, (size_t)(T + 1) * 8, cudaMemcpyDeviceToHost));
+        const size_t pitch = (size_t)va_glv_wide_block_doubles(e->desc.stepper) * 8;
+        if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {
-            if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + tt_len, (size_t)sadj * 64 * 8, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));
+            if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + 8, pitch, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));
             std::memcpy(x + (size_t)T * n, e->se_xf_host.data() + (size_t)b * n, (size_t)n * 8);
         }
     }

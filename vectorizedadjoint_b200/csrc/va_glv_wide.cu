@@ -4,20 +4,29 @@
 // f_i = x_i (r_i + (A x)_i), parameters [r, A row-major] (reference examples/GeneralizedLotkaVolterra/main.cpp:105-119).
 // The reference evaluates f and its vector-Jacobian products through AADC-recorded AVX kernels (lib/include/AadData.hpp
 // :175-210, :291-330), feeding all N^2+N parameters into the workspace for every call. Here the interaction matrix of a
-// trajectory is loaded ONCE into the register file of a 256-thread CTA and stays there:
+// trajectory is loaded into the register file of a 256-thread CTA and stays there for the whole sweep.
 //
+// Thread <-> data map. The 64x64 matrix is cut into 16x16 tiles of 4x4 (16 FP64 registers per thread). One tile
+// coordinate is the lane inside a 16-lane group (g), the other the group index (h). Along g a tile takes the entries
+// F(g,k) = 2g + (k&1) + 32(k>>1), so that the 16 lanes of a group read their vector operands as two conflict-free
+// LDS.128; along h it takes G(h,k) = 4h + k. With A in registers the scarce resource is the shared-memory / shuffle data path
+// (128 B/clk/SM, a quarter of what 64 DFMA/clk would need if every DFMA pulled a fresh 8-byte operand), so the map is
+// chosen to minimise operand traffic: a 4x4 tile needs 4 vector entries for 16 DFMA, and the partial sums are combined
+// by a recursive-halving exchange inside 16-lane groups (5 double shuffles, no shared memory):
 //   forward  (reference lib/include/detail/runge_kutta.hpp:76-118 + odeint controlled stepper):
-//       thread (i, q) owns a quarter of row i of A (16 FP64 registers); A x is 16 DFMA + two shuffle-adds per thread.
+//       p = tid/16, q = tid%16; y = A x: 16 DFMA, reduce over q inside the warp.
 //   backward (reference lib/include/detail/backpropagation.hpp:83-158, 231-254):
-//       thread (j, q) owns a quarter of COLUMN j of A and of the gradient accumulator Abar (16 + 16 registers);
-//       A^T v and the rank-1 update Abar += v x^T share the same 16 broadcast loads of v; nothing but v crosses warps.
+//       p = tid%16, q = tid/16 (transposed assignment, A re-read from L2); A^T v: 16 DFMA, reduce over p inside the
+//       warp; the rank-1 gradient update Abar += v x^T (16 DFMA) reuses the same operands; Abar lives in 16 registers.
+//   After either reduction lane g of a 16-lane group holds the entry 4*(tid/16) + g/4, so the SAME four lanes own a
+//   vector component in both sweeps and carry its scalar recurrences (stage state, slopes, stage adjoints).
 //
 // A persistent CTA integrates trajectory after trajectory (static stride over the batch), forward then backward, and
 // keeps its checkpoints in a private slab that is reused for every trajectory and therefore stays in L2.
 // Checkpoint policy: STORE_STAGES -- for every accepted step the stage states X_m and g_m = r + A X_m are kept, so the
 // reverse sweep needs no stage recompute (the reference recomputes them with s extra RHS calls per step,
-// detail/backpropagation.hpp:24-64); per step and trajectory that is 2*s*64*8 B of L2-resident traffic against
-// 6*4096 saved DFMA.
+// detail/backpropagation.hpp:24-64). The reverse sweep streams one step block (6 KB) at a time from the slab into
+// shared memory with TMA bulk copies (cp.async.bulk + mbarrier), double buffered, one step ahead.
 //
 // Accept/reject logic is odeint's (same error norm, same step-size rules). The matrix-vector products use FMA and a
 // tree reduction, so stage values differ from the scalar reference by round-off; accepted-step counts can therefore
@@ -27,7 +36,8 @@
 namespace {
 
 constexpr int NP = 64;   // padded species count
-constexpr int NT = 256;  // threads per CTA: 4 per row (forward) / per column (backward)
+constexpr int NT = 256;  // threads per CTA = 16 x 16 tiles of 4 x 4
+constexpr int HDR = 8;   // doubles in a step-block header (hdr[0] = t_n)
 
 // ---- compile-time tableaux: zero weights vanish from the unrolled code --------------------------------------------
 struct TabRK4 {
@@ -92,6 +102,9 @@ struct TabDOPRI5 {
     }
 };
 
+template <class Tab>
+constexpr int block_doubles() { return HDR + 2 * Tab::SADJ * NP; }
+
 // e^(-1/P) for e > 0: float seed + Newton on y^-P = e (quadratic), accurate to a few ulp; replaces pow() in
 // odeint's default_step_adjuster on this path (all 256 threads evaluate it redundantly, so it has to be short).
 template <int P>
@@ -111,107 +124,156 @@ __device__ __forceinline__ double inv_root(double e)
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-struct SlabView {
-    double *tt; // [cap+2]
-    double *sx; // [cap*SADJ][NP] stage states X_m of accepted steps
-    double *sg; // [cap*SADJ][NP] g_m = r + A X_m
-};
+// Combine the four partial sums of a 4x4 tile over the 16 lanes of a group (recursive halving: 2+1+1+1 double shuffles,
+// no selects). Precondition: the tile is held PERMUTED -- lane g keeps, in register k, the partial sum for tile entry
+// R^k with R = g>>2 (the permutation is applied once per trajectory when the tile is loaded). Lane g returns the
+// complete sum for tile entry R.
+__device__ __forceinline__ double reduce16(double s0, double s1, double s2, double s3)
+{
+    double k0 = s0 + shfl_xor_d(s2, 8);
+    const double k1 = s1 + shfl_xor_d(s3, 8);
+    k0 += shfl_xor_d(k1, 4);
+    k0 += shfl_xor_d(k0, 2);
+    k0 += shfl_xor_d(k0, 1);
+    return k0;
+}
+
+// conditional swap used to permute a freshly loaded tile (once per trajectory and sweep)
+__device__ __forceinline__ void cswap(bool c, double &u, double &v)
+{
+    const double t = c ? v : u;
+    v = c ? u : v;
+    u = t;
+}
+
+// ---- mbarrier + TMA bulk copy (global -> shared) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <class Tab, bool ADAPTIVE, bool EXACT64>
 __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
-    __shared__ __align__(16) double xs[2][NP];
+    constexpr int BLK = block_doubles<Tab>();
+    __shared__ __align__(16) double xs[2][NP];      // stage state (forward) / v = w o x (backward), double buffered
+    __shared__ __align__(128) double xg[2][BLK];    // step blocks [hdr | X_0..X_{s-1} | g_0..g_{s-1}] streamed back by TMA
     __shared__ double red[8];
+    __shared__ __align__(8) uint64_t mbar[2];
 
     const int tid = threadIdx.x;
-    const int q = tid & 3;     // quarter
-    const int rc = tid >> 2;   // row (forward) / column (backward) owned by this thread
+    const int g16 = tid & 15;        // lane inside the 16-lane reduction group (q forward, p backward)
+    const int hi = tid >> 4;         // the other tile coordinate (p forward, q backward)
+    const int own = 4 * hi + (g16 >> 2); // vector component owned by this lane (4 redundant lanes per component)
+    const bool writer = (tid & 3) == 0;
     const int lane = tid & 31, warp = tid >> 5;
     const int n = a.n;
     const int npar = n * n + n;
     const int cap = a.cap;
+    double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
 
-    SlabView sl;
-    {
-        double *base = a.slab + (int64_t)blockIdx.x * a.slab_stride;
-        const int tt_len = (cap + 2 + 15) & ~15;
-        sl.tt = base;
-        sl.sx = base + tt_len;
-        sl.sg = sl.sx + (int64_t)cap * SADJ * NP;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    uint32_t mbar_parity = 0; // bit b: parity of the next completion of mbar[b]
 
-    // gradient accumulators (backward layout); persistent across trajectories when the caller wants the sum
-    double Abar[16], rbar = 0.0;
+    // gradient accumulators (backward tile); persistent across trajectories when the caller wants the sum
+    double Abar[4][4], rbar = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) Abar[k] = 0.0;
-
-    int call = 0; // parity of the xs double buffer
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Abar[r][c] = 0.0;
 
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
         const double *pb = a.params + b * npar;
 
         // ================================ forward sweep =====================================
-        double Ar[16];
-        double r_i = 0.0, x = 0.0;
+        double At[4][4];
+        double r_own = 0.0, x = 0.0;
         {
-            const int i = rc;
-            if (EXACT64) {
-                const double2 *row = reinterpret_cast<const double2 *>(pb + NP + i * NP);
+            // forward tile: rows G(hi,.) = 4hi + k, columns F(g16,.) = 2g16 + (c&1) + 32(c>>1)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const double2 v = __ldg(row + 4 * k + q);
-                    Ar[2 * k] = v.x;
-                    Ar[2 * k + 1] = v.y;
-                }
-                r_i = __ldg(pb + i);
-                x = __ldg(a.x0 + b * NP + i);
-            } else {
+            for (int r = 0; r < 4; ++r) {
+                const int row = 4 * hi + r;
+                if (EXACT64) {
+                    const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 2 * g16);
+                    const double2 v0 = __ldg(src), v1 = __ldg(src + 16);
+                    At[r][0] = v0.x; At[r][1] = v0.y; At[r][2] = v1.x; At[r][3] = v1.y;
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int col = 8 * k + 2 * q + e;
-                        Ar[2 * k + e] = (i < n && col < n) ? __ldg(pb + n + i * n + col) : 0.0;
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = 2 * g16 + (c & 1) + 32 * (c >> 1);
+                        At[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
                     }
                 }
-                if (i < n) { r_i = __ldg(pb + i); x = __ldg(a.x0 + b * n + i); }
             }
+            // register k <- tile row R^k (see reduce16)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                cswap(g16 & 4, At[0][c], At[1][c]);
+                cswap(g16 & 4, At[2][c], At[3][c]);
+                cswap(g16 & 8, At[0][c], At[2][c]);
+                cswap(g16 & 8, At[1][c], At[3][c]);
+            }
+            if (own < n) { r_own = __ldg(pb + own); x = __ldg(a.x0 + b * n + own); }
         }
 
-        // g = r_i + (A X)_i for the row of this thread; X is this row's entry of the stage state
-        auto matvec = [&](double X) -> double {
-            double *buf = xs[call & 1];
-            ++call;
-            if (q == 0) buf[rc] = X;
+        // g = r_own + (A X)_own ; X is this lane's component of the stage state
+        auto matvec = [&](double X, int m) -> double { // m: stage index, compile-time after unrolling -> fixed buffer
+            double *buf = xs[m & 1];
+            if (writer) buf[own] = X;
             __syncthreads();
-            const double2 *xv = reinterpret_cast<const double2 *>(buf);
-            double acc0 = (q == 0) ? r_i : 0.0, acc1 = 0.0;
+            const double2 *xv = reinterpret_cast<const double2 *>(buf + 2 * g16);
+            const double2 x01 = xv[0], x23 = xv[16];
+            double s[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double2 xx = xv[4 * k + q];
-                acc0 = fma(Ar[2 * k], xx.x, acc0);
-                acc1 = fma(Ar[2 * k + 1], xx.y, acc1);
-            }
-            double g = acc0 + acc1;
-            g += shfl_xor_d(g, 1);
-            g += shfl_xor_d(g, 2);
-            return g;
+            for (int r = 0; r < 4; ++r) s[r] = fma(At[r][3], x23.y, fma(At[r][2], x23.x, fma(At[r][1], x01.y, At[r][0] * x01.x)));
+            return r_own + reduce16(s[0], s[1], s[2], s[3]);
         };
 
         double t = a.ti, dt = a.dt0;
         const double tf = a.tf;
         int nck = 0, rejects = 0, status = 0;
         double K[S];
-        double g0 = matvec(x);
+        double g0 = matvec(x, 0);
         K[0] = x * g0;
 
         auto store_stage = [&](int m, double X, double g) {
-            if (q == 0) {
-                const int64_t o = ((int64_t)nck * SADJ + m) * NP + rc;
-                sl.sx[o] = X;
-                sl.sg[o] = g;
+            if (writer) {
+                double *blk = slab + (int64_t)nck * BLK + HDR;
+                blk[m * NP + own] = X;
+                blk[(SADJ + m) * NP + own] = g;
             }
         };
 
@@ -222,20 +284,19 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
             if (fresh) {
                 if (nck >= cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
                 store_stage(0, x, g0);
-                if (tid == 0) sl.tt[nck] = t;
+                if (tid == 0) slab[(int64_t)nck * BLK] = t;
                 if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
                 trials = 0;
                 fresh = false;
             }
-            // stages
 #pragma unroll
             for (int m = 1; m < SE; ++m) {
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < m; ++j)
-                    if (Tab::a(m, j) != 0.0) acc = fma(Tab::a(m, j), K[j], acc);
+                    if (Tab::a(m, j) != 0.0) acc = fma(a.coef.a[m][j], K[j], acc);
                 const double X = fma(dt, acc, x);
-                const double g = matvec(X);
+                const double g = matvec(X, m);
                 K[m] = X * g;
                 if (m < SADJ) store_stage(m, X, g);
             }
@@ -244,12 +305,12 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < SE; ++j)
-                    if (Tab::b(j) != 0.0) acc = fma(Tab::b(j), K[j], acc);
+                    if (Tab::b(j) != 0.0) acc = fma(a.coef.b[j], K[j], acc);
                 xnew = fma(dt, acc, x);
             }
             double g_last = 0.0;
             if (Tab::FSAL) {
-                g_last = matvec(xnew);
+                g_last = matvec(xnew, S - 1);
                 K[S - 1] = xnew * g_last;
             }
             bool accept = true;
@@ -258,7 +319,7 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < S; ++j)
-                    if (Tab::db(j) != 0.0) acc = fma(Tab::db(j), K[j], acc);
+                    if (Tab::db(j) != 0.0) acc = fma(a.coef.db[j], K[j], acc);
                 const double xerr = dt * acc;
                 // default_error_checker::error, max norm over species
                 double e = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
@@ -300,35 +361,51 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                     g0 = g_last;
                     K[0] = K[S - 1];
                 } else if (active) {
-                    g0 = matvec(x);
+                    g0 = matvec(x, 0);
                     K[0] = x * g0;
                 }
             }
         }
         const int T = nck;
-        if (tid == 0) sl.tt[T] = t;
+        if (tid == 0) slab[(int64_t)T * BLK] = t; // header of block T carries the final time
         if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
-        status = __syncthreads_or(status); // also orders the slab writes before the reverse sweep reads them
+        fence_proxy_async();               // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
+        status = __syncthreads_or(status);
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
-        if (q == 0 && rc < n) a.x_final[b * n + rc] = failed ? nan("") : x;
+        if (writer && own < n) a.x_final[b * n + own] = failed ? nan("") : x;
         if (tid == 0) {
             if (a.n_accept) a.n_accept[b] = T;
             if (a.n_reject) a.n_reject[b] = rejects;
             if (a.status) a.status[b] = status;
         }
-        // x(tf) by column for the seeds: exchange through shared memory (row owner -> column owner is the same index)
-        const double x_tf = x; // thread (rc, q): forward row rc == backward column rc
+        const double x_tf = x, t_final = t;
 
         // ================================ reverse sweep =====================================
-        const int j = rc;
-        double Ac[16];
+        // transposed tile assignment: p = g16 (rows), q = hi (columns); the owned component stays `own`
+        // transposed tile assignment: rows F(g16,.), columns G(hi,.) = 4hi + c; the owned component stays `own`
+        if (a.n_out > 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+            for (int r = 0; r < 4; ++r) {
+                const int row = 2 * g16 + (r & 1) + 32 * (r >> 1);
+                if (EXACT64) {
+                    const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 4 * hi);
+                    const double2 v0 = __ldg(src), v1 = __ldg(src + 1);
+                    At[r][0] = v0.x; At[r][1] = v0.y; At[r][2] = v1.x; At[r][3] = v1.y;
+                } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int row = 8 * k + 2 * q + e;
-                if (EXACT64) Ac[2 * k + e] = __ldg(pb + NP + row * NP + j);
-                else Ac[2 * k + e] = (row < n && j < n) ? __ldg(pb + n + row * n + j) : 0.0;
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = 4 * hi + c;
+                        At[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                    }
+                }
+            }
+            // register k <- tile column R^k
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                cswap(g16 & 4, At[r][0], At[r][1]);
+                cswap(g16 & 4, At[r][2], At[r][3]);
+                cswap(g16 & 8, At[r][0], At[r][2]);
+                cswap(g16 & 8, At[r][1], At[r][3]);
             }
         }
 
@@ -336,108 +413,127 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
             double *lam_io = a.lambda + (b * a.n_out + o) * n;
             double *mu_o = a.mu + (a.reduce == VA_REDUCE_SUM ? (int64_t)o : (b * a.n_out + o)) * npar;
             if (failed) {
-                if (q == 0 && j < n) lam_io[j] = nan("");
+                if (writer && own < n) lam_io[own] = nan("");
                 if (a.reduce == VA_REDUCE_NONE)
                     for (int k = tid; k < npar; k += NT) mu_o[k] = nan("");
                 continue;
             }
             double lam;
-            if (a.objective == VA_OBJ_SUM) lam = (j < n) ? 1.0 : 0.0;
+            if (a.objective == VA_OBJ_SUM) lam = (own < n) ? 1.0 : 0.0;
             else if (a.objective == VA_OBJ_HALF_NORM2) lam = x_tf;
-            else lam = (j < n) ? lam_io[j] : 0.0;
+            else lam = (own < n) ? lam_io[own] : 0.0;
 
             if (a.reduce == VA_REDUCE_NONE) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) Abar[k] = 0.0;
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Abar[r][c] = 0.0;
                 rbar = 0.0;
             }
 
-            // flattened (step, stage) index, descending; two-deep register prefetch of X and g from the slab
-            int idx = T * SADJ - 1;
-            double Xn0 = 0, gn0 = 0, Xn1 = 0, gn1 = 0;
-            if (idx >= 0) { Xn0 = sl.sx[(int64_t)idx * NP + j]; gn0 = sl.sg[(int64_t)idx * NP + j]; }
-            if (idx >= 1) { Xn1 = sl.sx[(int64_t)(idx - 1) * NP + j]; gn1 = sl.sg[(int64_t)(idx - 1) * NP + j]; }
-            double t_hi = (T > 0) ? sl.tt[T] : 0.0;
+            // stream the step blocks back, newest first; block `step` -> buffer (T-1-step)&1, fetched one step ahead
+            if (o > 0) __syncthreads(); // the previous seed's last reads of xg[] are done before it is refilled
+            if (T > 0 && tid == 0) {
+                mbar_expect_tx(&mbar[0], BLK * 8);
+                bulk_g2s(xg[0], slab + (int64_t)(T - 1) * BLK, BLK * 8, &mbar[0]);
+            }
+            double t_hi = t_final;
             for (int step = T - 1; step >= 0; --step) {
-                const double t_lo = sl.tt[step];
-                const double dt_s = t_hi - t_lo; // StateStorage::GetDt
+                const int bufi = (T - 1 - step) & 1;
+                mbar_wait(&mbar[bufi], (mbar_parity >> bufi) & 1);
+                mbar_parity ^= 1u << bufi;
+                const double *blk = xg[bufi];
+                const double t_lo = blk[0];
+                const double dt_s = t_hi - t_lo; // StateStorage::GetDt: difference of the stored times
                 t_hi = t_lo;
                 double W[SADJ + 1];
                 W[0] = lam;
 #pragma unroll
-                for (int m = 1; m <= SADJ; ++m) W[m] = (Tab::b(m - 1) * dt_s) * lam;
+                for (int m = 1; m <= SADJ; ++m) W[m] = Tab::b(m - 1) != 0.0 ? (a.coef.b[m - 1] * dt_s) * lam : 0.0;
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
-                    const double X = Xn0, g = gn0;
-                    Xn0 = Xn1; gn0 = gn1;
-                    if (idx >= 2) {
-                        Xn1 = sl.sx[(int64_t)(idx - 2) * NP + j];
-                        gn1 = sl.sg[(int64_t)(idx - 2) * NP + j];
-                    }
-                    --idx;
-                    const bool live = (m == SADJ) || true; // every stage runs a VJP (detail/backpropagation.hpp:201-223)
-                    (void)live;
-                    const double v = W[m] * X;
-                    double *buf = xs[call & 1];
-                    ++call;
-                    if (q == 0) buf[j] = v;
+                    const double Xo = blk[HDR + (m - 1) * NP + own];
+                    const double go = blk[HDR + (SADJ + m - 1) * NP + own];
+                    const double v = W[m] * Xo;
+                    double *vb = xs[m & 1];
+                    if (writer) vb[own] = v;
                     __syncthreads();
-                    const double2 *vv2 = reinterpret_cast<const double2 *>(buf);
-                    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const double2 vv = vv2[4 * k + q];
-                        acc0 = fma(Ac[2 * k], vv.x, acc0);
-                        acc1 = fma(Ac[2 * k + 1], vv.y, acc1);
-                        Abar[2 * k] = fma(vv.x, X, Abar[2 * k]);
-                        Abar[2 * k + 1] = fma(vv.y, X, Abar[2 * k + 1]);
+                    if (m == SADJ && step > 0 && tid == 0) {
+                        // every thread is past its reads of the other buffer (previous step): refill it
+                        mbar_expect_tx(&mbar[bufi ^ 1], BLK * 8);
+                        bulk_g2s(xg[bufi ^ 1], slab + (int64_t)(step - 1) * BLK, BLK * 8, &mbar[bufi ^ 1]);
                     }
-                    double sum = acc0 + acc1;
-                    sum += shfl_xor_d(sum, 1);
-                    sum += shfl_xor_d(sum, 2);
-                    const double gx = fma(W[m], g, sum);
+                    const double2 *vv2 = reinterpret_cast<const double2 *>(vb + 2 * g16);
+                    const double2 *xx2 = reinterpret_cast<const double2 *>(blk + HDR + (m - 1) * NP + 4 * hi);
+                    const double2 v01 = vv2[0], v23 = vv2[16], x01 = xx2[0], x23 = xx2[1];
+                    const double vr[4] = {v01.x, v01.y, v23.x, v23.y};
+                    const double xc[4] = {x01.x, x01.y, x23.x, x23.y};
+                    double s[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[c] = fma(At[3][c], vr[3], fma(At[2][c], vr[2], fma(At[1][c], vr[1], At[0][c] * vr[0])));
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) Abar[r][c] = fma(vr[r], xc[c], Abar[r][c]);
+                    const double sum = reduce16(s[0], s[1], s[2], s[3]); // (A^T v)_own
+                    const double gx = fma(W[m], go, sum);
                     rbar += v;
                     W[0] += gx;
 #pragma unroll
                     for (int k = 1; k < m; ++k)
-                        if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gx * Tab::a(m - 1, k - 1), dt_s, W[k]);
+                        if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gx * a.coef.a[m - 1][k - 1], dt_s, W[k]);
                 }
                 lam = W[0];
             }
-            if (q == 0 && j < n) lam_io[j] = lam;
+            if (writer && own < n) lam_io[own] = lam;
             if (a.reduce == VA_REDUCE_NONE) {
-                if (q == 0 && j < n) mu_o[j] = rbar;
+                if (writer && own < n) mu_o[own] = rbar;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int r = 0; r < 4; ++r) {
+                    const int row = 2 * g16 + (r & 1) + 32 * (r >> 1);
+                    if (EXACT64) {
+                        double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP + 4 * hi);
+                        dst[0] = make_double2(Abar[r][0], Abar[r][1]);
+                        dst[1] = make_double2(Abar[r][2], Abar[r][3]);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int row = 8 * k + 2 * q + e;
-                        if (row < n && j < n) mu_o[n + row * n + j] = Abar[2 * k + e];
+                        for (int c = 0; c < 4; ++c) {
+                            const int col = 4 * hi + c;
+                            if (row < n && col < n) mu_o[n + row * n + col] = Abar[r][c];
+                        }
                     }
                 }
             }
         }
-        __syncthreads(); // slab is reused by the next trajectory
+        __syncthreads(); // slab and shared buffers are reused by the next trajectory
     }
 
     if (a.reduce == VA_REDUCE_SUM) {
         double *part = a.partial + (int64_t)blockIdx.x * npar;
-        const int j = rc;
-        if (q == 0 && j < n) part[j] = rbar;
+        if (writer && own < n) part[own] = rbar;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int r = 0; r < 4; ++r) {
+            const int row = 2 * g16 + (r & 1) + 32 * (r >> 1);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int row = 8 * k + 2 * q + e;
-                if (row < n && j < n) part[n + row * n + j] = Abar[2 * k + e];
+            for (int c = 0; c < 4; ++c) {
+                const int col = 4 * hi + c;
+                if (row < n && col < n) part[n + row * n + col] = Abar[r][c];
             }
         }
     }
 }
 
 template <class Tab, bool ADAPTIVE>
-cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st)
+cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
 {
+    VaGlvWideArgs a = a_in;
+    // tableau values travel in the kernel arguments (constant bank): DFMA takes them as c[bank][offset] operands,
+    // while the compile-time copy in Tab:: only decides which terms exist
+    for (int m = 0; m < Tab::S; ++m) {
+        for (int j = 0; j < m && j < 6; ++j) a.coef.a[m][j] = Tab::a(m, j);
+        a.coef.b[m] = Tab::b(m);
+        a.coef.db[m] = Tab::db(m);
+    }
     if (a.n == NP) k_glv_wide<Tab, ADAPTIVE, true><<<a.grid, NT, 0, st>>>(a);
     else k_glv_wide<Tab, ADAPTIVE, false><<<a.grid, NT, 0, st>>>(a);
     return cudaGetLastError();
@@ -450,12 +546,12 @@ cudaError_t occupancy(int n, int *ctas_per_sm)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, false>, NT, 0);
 }
 
-int sadj_of(int stepper)
+int block_of(int stepper)
 {
     switch (stepper) {
-    case VA_RK_RK4: return TabRK4::SADJ;
-    case VA_RK_CK54: return TabCK54::SADJ;
-    case VA_RK_DOPRI5: return TabDOPRI5::SADJ;
+    case VA_RK_RK4: return block_doubles<TabRK4>();
+    case VA_RK_CK54: return block_doubles<TabCK54>();
+    case VA_RK_DOPRI5: return block_doubles<TabDOPRI5>();
     }
     return 0;
 }
@@ -470,11 +566,12 @@ bool va_glv_wide_supported(int n, int stepper, int adaptive)
     return false;
 }
 
+int va_glv_wide_block_doubles(int stepper) { return block_of(stepper); }
+
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap)
 {
     (void)n;
-    const int64_t tt_len = (cap + 2 + 15) & ~15;
-    return tt_len + 2 * (int64_t)cap * sadj_of(stepper) * NP;
+    return (int64_t)(cap + 1) * block_of(stepper); // block T holds only the final time in its header
 }
 
 cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads)
