@@ -1,0 +1,8 @@
+set -e
+for LG in 8 16; do
+  rm -f vectorizedadjoint_b200/csrc/build/va_glv_wide.o
+  make -s -C vectorizedadjoint_b200/csrc GLV_LG=$LG -j8 > /dev/null
+  echo "== LG=$LG"
+  timeout 600 python -m pytest tests -m gpu -q -k "glv" 2>&1 | tail -2
+  python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['clocks'])"
+done

@@ -33,10 +33,13 @@
 // flip only when the error estimate is within ~1e-8 relative of a threshold (documented in DESIGN.md).
 #include "va_common.cuh"
 
+#ifndef VA_GLV_LG
+#define VA_GLV_LG 8
+#endif
+
 namespace {
 
 constexpr int NP = 64;   // padded species count
-constexpr int NT = 256;  // threads per CTA = 16 x 16 tiles of 4 x 4
 constexpr int HDR = 8;   // doubles in a step-block header (hdr[0] = t_n)
 
 // ---- compile-time tableaux: zero weights vanish from the unrolled code --------------------------------------------
@@ -124,17 +127,19 @@ __device__ __forceinline__ double inv_root(double e)
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Combine the four partial sums of a 4x4 tile over the 16 lanes of a group (recursive halving: 2+1+1+1 double shuffles,
-// no selects). Precondition: the tile is held PERMUTED -- lane g keeps, in register k, the partial sum for tile entry
-// R^k with R = g>>2 (the permutation is applied once per trajectory when the tile is loaded). Lane g returns the
-// complete sum for tile entry R.
-__device__ __forceinline__ double reduce16(double s0, double s1, double s2, double s3)
+// Combine the four partial sums of a tile over the LG lanes of a reduction group by recursive halving (2+1 double
+// shuffles that halve the data, then log2(LG)-2 butterflies), no selects. Precondition: the tile is held PERMUTED --
+// lane g keeps, in register k, the partial sum for tile entry R^k with R = g / (LG/4) (the permutation is applied once
+// per trajectory when the tile is loaded). Lane g returns the complete sum for tile entry R; the LG/4 lanes that share
+// R end up with bit-identical values (they take control decisions together).
+template <int LG>
+__device__ __forceinline__ double reduce_group(double s0, double s1, double s2, double s3)
 {
-    double k0 = s0 + shfl_xor_d(s2, 8);
-    const double k1 = s1 + shfl_xor_d(s3, 8);
-    k0 += shfl_xor_d(k1, 4);
-    k0 += shfl_xor_d(k0, 2);
-    k0 += shfl_xor_d(k0, 1);
+    double k0 = s0 + shfl_xor_d(s2, LG / 2);
+    const double k1 = s1 + shfl_xor_d(s3, LG / 2);
+    k0 += shfl_xor_d(k1, LG / 4);
+#pragma unroll
+    for (int d = LG / 8; d >= 1; d >>= 1) k0 += shfl_xor_d(k0, d);
     return k0;
 }
 
@@ -178,27 +183,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <class Tab, bool ADAPTIVE, bool EXACT64>
-__global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
+// LG = lanes per reduction group: 16 -> 256 threads, 4x4 tiles; 8 -> 128 threads, 4x8 / 8x4 tiles (fewer operand and
+// shuffle wavefronts per DFMA, twice the registers per thread).
+template <class Tab, bool ADAPTIVE, bool EXACT64, int LG>
+__global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
 {
+    constexpr int NT = 16 * LG;      // threads per CTA
+    constexpr int TG = NP / LG;      // tile extent along the lane (g) direction: 4 or 8
+    constexpr int NW = NT / 32;
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
     constexpr int BLK = block_doubles<Tab>();
     __shared__ __align__(16) double xs[2][NP];      // stage state (forward) / v = w o x (backward), double buffered
     __shared__ __align__(128) double xg[2][BLK];    // step blocks [hdr | X_0..X_{s-1} | g_0..g_{s-1}] streamed back by TMA
-    __shared__ double red[8];
+    __shared__ double red[NW];
     __shared__ __align__(8) uint64_t mbar[2];
 
     const int tid = threadIdx.x;
-    const int g16 = tid & 15;        // lane inside the 16-lane reduction group (q forward, p backward)
-    const int hi = tid >> 4;         // the other tile coordinate (p forward, q backward)
-    const int own = 4 * hi + (g16 >> 2); // vector component owned by this lane (4 redundant lanes per component)
-    const bool writer = (tid & 3) == 0;
+    const int g = tid & (LG - 1);    // lane inside the reduction group (column tile forward, row tile backward)
+    const int hi = tid / LG;         // the other tile coordinate, 0..15 (row tile forward, column tile backward)
+    const int R = g / (LG / 4);      // tile entry (of 4) this lane ends up with after a reduction
+    const int own = 4 * hi + R;      // vector component owned by this lane (LG/4 redundant lanes per component)
+    const bool writer = (g & (LG / 4 - 1)) == 0;
+    const bool sw_lo = g & (LG / 4), sw_hi = g & (LG / 2); // permutation bits of R
     const int lane = tid & 31, warp = tid >> 5;
     const int n = a.n;
     const int npar = n * n + n;
     const int cap = a.cap;
     double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
+
+    // g-direction entries of a tile: FG(e) = 2g + (e&1) + 2 LG (e>>1): the LG lanes of a group read their operands
+    // as TG/2 conflict-free LDS.128 (double2 index g + LG j)
+    auto FG = [&](int e) { return 2 * g + (e & 1) + 2 * LG * (e >> 1); };
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -208,10 +224,10 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
     __syncthreads();
     uint32_t mbar_parity = 0; // bit b: parity of the next completion of mbar[b]
 
-    // gradient accumulators (backward tile); persistent across trajectories when the caller wants the sum
-    double Abar[4][4], rbar = 0.0;
+    // gradient accumulators (backward tile: TG rows x 4 columns); persistent across trajectories in summed mode
+    double Abar[TG][4], rbar = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < TG; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) Abar[r][c] = 0.0;
 
@@ -219,61 +235,76 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
         const double *pb = a.params + b * npar;
 
         // ================================ forward sweep =====================================
-        double At[4][4];
+        // forward tile: 4 rows 4hi + k (held permuted: register k <- row R^k), TG columns FG(c)
+        double Af[4][TG];
         double r_own = 0.0, x = 0.0;
         {
-            // forward tile: rows G(hi,.) = 4hi + k, columns F(g16,.) = 2g16 + (c&1) + 32(c>>1)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int row = 4 * hi + r;
                 if (EXACT64) {
-                    const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 2 * g16);
-                    const double2 v0 = __ldg(src), v1 = __ldg(src + 16);
-                    At[r][0] = v0.x; At[r][1] = v0.y; At[r][2] = v1.x; At[r][3] = v1.y;
+                    const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 2 * g);
+#pragma unroll
+                    for (int j = 0; j < TG / 2; ++j) {
+                        const double2 v = __ldg(src + LG * j);
+                        Af[r][2 * j] = v.x;
+                        Af[r][2 * j + 1] = v.y;
+                    }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int col = 2 * g16 + (c & 1) + 32 * (c >> 1);
-                        At[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                    for (int c = 0; c < TG; ++c) {
+                        const int col = FG(c);
+                        Af[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
                     }
                 }
             }
-            // register k <- tile row R^k (see reduce16)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                cswap(g16 & 4, At[0][c], At[1][c]);
-                cswap(g16 & 4, At[2][c], At[3][c]);
-                cswap(g16 & 8, At[0][c], At[2][c]);
-                cswap(g16 & 8, At[1][c], At[3][c]);
+            for (int c = 0; c < TG; ++c) {
+                cswap(sw_lo, Af[0][c], Af[1][c]);
+                cswap(sw_lo, Af[2][c], Af[3][c]);
+                cswap(sw_hi, Af[0][c], Af[2][c]);
+                cswap(sw_hi, Af[1][c], Af[3][c]);
             }
             if (own < n) { r_own = __ldg(pb + own); x = __ldg(a.x0 + b * n + own); }
         }
 
-        // g = r_own + (A X)_own ; X is this lane's component of the stage state
-        auto matvec = [&](double X, int m) -> double { // m: stage index, compile-time after unrolling -> fixed buffer
+        // sum = (A X)_own for the stage state whose own-component is X. `extra` runs between the operand loads and
+        // the reduction: work that does not depend on the result is issued there, off the critical path.
+        auto matvec = [&](double X, int m, auto &&extra) -> double { // m is a compile-time constant after unrolling
             double *buf = xs[m & 1];
             if (writer) buf[own] = X;
             __syncthreads();
-            const double2 *xv = reinterpret_cast<const double2 *>(buf + 2 * g16);
-            const double2 x01 = xv[0], x23 = xv[16];
+            const double2 *xv = reinterpret_cast<const double2 *>(buf) + g;
+            double xc[TG];
+#pragma unroll
+            for (int j = 0; j < TG / 2; ++j) {
+                const double2 v = xv[LG * j];
+                xc[2 * j] = v.x;
+                xc[2 * j + 1] = v.y;
+            }
             double s[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) s[r] = fma(At[r][3], x23.y, fma(At[r][2], x23.x, fma(At[r][1], x01.y, At[r][0] * x01.x)));
-            return r_own + reduce16(s[0], s[1], s[2], s[3]);
+            for (int r = 0; r < 4; ++r) s[r] = Af[r][0] * xc[0];
+#pragma unroll
+            for (int c = 1; c < TG; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s[r] = fma(Af[r][c], xc[c], s[r]);
+            extra();
+            return reduce_group<LG>(s[0], s[1], s[2], s[3]);
         };
 
         double t = a.ti, dt = a.dt0;
         const double tf = a.tf;
         int nck = 0, rejects = 0, status = 0;
         double K[S];
-        double g0 = matvec(x, 0);
+        double g0 = r_own + matvec(x, 0, [] {});
         K[0] = x * g0;
 
-        auto store_stage = [&](int m, double X, double g) {
+        auto store_stage = [&](int m, double X, double gg) {
             if (writer) {
                 double *blk = slab + (int64_t)nck * BLK + HDR;
                 blk[m * NP + own] = X;
-                blk[(SADJ + m) * NP + own] = g;
+                blk[(SADJ + m) * NP + own] = gg;
             }
         };
 
@@ -289,47 +320,59 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                 trials = 0;
                 fresh = false;
             }
+            // Stage m produces K_m = X_m (r + A X_m). The state of the NEXT stage (or the new solution after the last
+            // one), Y = x + dt sum_{j<=m} c_j K_j, is split so that only ONE DFMA follows the reduction:
+            //   Y = fma(c1, sum, base),  c1 = dt c_m X_m,  base = x + dt sum_{j<m} c_j K_j + c1 r   (all known early).
+            double X = fma(dt * a.coef.a[1][0], K[0], x);
+            double perr = 0.0; // sum_{j<SE-1} db_j K_j
 #pragma unroll
             for (int m = 1; m < SE; ++m) {
-                double acc = 0.0;
+                const bool last = (m == SE - 1);
+                double c1 = 0.0, base = 0.0;
+                const double sum = matvec(X, m, [&] {
+                    double acc = 0.0;
 #pragma unroll
-                for (int j = 0; j < m; ++j)
-                    if (Tab::a(m, j) != 0.0) acc = fma(a.coef.a[m][j], K[j], acc);
-                const double X = fma(dt, acc, x);
-                const double g = matvec(X, m);
-                K[m] = X * g;
-                if (m < SADJ) store_stage(m, X, g);
-            }
-            double xnew;
-            {
-                double acc = 0.0;
+                    for (int j = 0; j < m; ++j) {
+                        const double cz = last ? Tab::b(j) : Tab::a(m + 1, j);
+                        if (cz != 0.0) acc = fma(last ? a.coef.b[j] : a.coef.a[m + 1][j], K[j], acc);
+                    }
+                    const double cm = last ? Tab::b(m) : Tab::a(m + 1, m);
+                    c1 = (cm != 0.0) ? (dt * (last ? a.coef.b[m] : a.coef.a[m + 1][m])) * X : 0.0;
+                    base = fma(c1, r_own, fma(dt, acc, x));
+                    if (last && ADAPTIVE) {
 #pragma unroll
-                for (int j = 0; j < SE; ++j)
-                    if (Tab::b(j) != 0.0) acc = fma(a.coef.b[j], K[j], acc);
-                xnew = fma(dt, acc, x);
+                        for (int j = 0; j < m; ++j)
+                            if (Tab::db(j) != 0.0) perr = fma(a.coef.db[j], K[j], perr);
+                    }
+                });
+                const double Y = fma(c1, sum, base);
+                const double gg = r_own + sum;
+                K[m] = X * gg;
+                if (m < SADJ) store_stage(m, X, gg);
+                X = Y;
             }
+            const double xnew = X;
             double g_last = 0.0;
             if (Tab::FSAL) {
-                g_last = matvec(xnew, S - 1);
+                g_last = r_own + matvec(xnew, S - 1, [] {});
                 K[S - 1] = xnew * g_last;
             }
             bool accept = true;
             double err = 0.0;
             if (ADAPTIVE) {
-                double acc = 0.0;
+                double acc = perr;
 #pragma unroll
-                for (int j = 0; j < S; ++j)
+                for (int j = SE - 1; j < S; ++j)
                     if (Tab::db(j) != 0.0) acc = fma(a.coef.db[j], K[j], acc);
                 const double xerr = dt * acc;
                 // default_error_checker::error, max norm over species
                 double e = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
-                e = fmax(e, shfl_xor_d(e, 4));
-                e = fmax(e, shfl_xor_d(e, 8));
-                e = fmax(e, shfl_xor_d(e, 16));
+#pragma unroll
+                for (int d = 16; d >= LG / 4; d >>= 1) e = fmax(e, shfl_xor_d(e, d));
                 if (lane == 0) red[warp] = e;
                 __syncthreads();
 #pragma unroll
-                for (int w = 0; w < 8; ++w) err = fmax(err, red[w]);
+                for (int w = 0; w < NW; ++w) err = fmax(err, red[w]);
                 accept = !(err > 1.0);
             }
             if (!accept) {
@@ -348,8 +391,8 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                         double floor_ = 1.0;
 #pragma unroll
                         for (int k = 0; k < P; ++k) floor_ *= 0.2; // 5^-P
-                        err = fmax(floor_, err);
-                        dt *= 9.0 / 10.0 * inv_root<P>(err);
+                        // err <= 5^-P: the growth factor is exactly 0.9 * 5 (pow(5^-P, -1/P) == 5 in glibc as well)
+                        dt *= (err <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root<P>(err);
                     }
                     active = va_less_with_sign(t, tf, dt);
                 } else {
@@ -361,7 +404,7 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                     g0 = g_last;
                     K[0] = K[S - 1];
                 } else if (active) {
-                    g0 = matvec(x, 0);
+                    g0 = r_own + matvec(x, 0, [] {});
                     K[0] = x * g0;
                 }
             }
@@ -381,31 +424,31 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
         const double x_tf = x, t_final = t;
 
         // ================================ reverse sweep =====================================
-        // transposed tile assignment: p = g16 (rows), q = hi (columns); the owned component stays `own`
-        // transposed tile assignment: rows F(g16,.), columns G(hi,.) = 4hi + c; the owned component stays `own`
+        // transposed tile: TG rows FG(r), 4 columns 4hi + k (held permuted: register k <- column R^k); the owned
+        // component stays `own`. A is re-read (L2 hit).
+        double Ab[TG][4];
         if (a.n_out > 0) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int row = 2 * g16 + (r & 1) + 32 * (r >> 1);
+            for (int r = 0; r < TG; ++r) {
+                const int row = FG(r);
                 if (EXACT64) {
                     const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 4 * hi);
                     const double2 v0 = __ldg(src), v1 = __ldg(src + 1);
-                    At[r][0] = v0.x; At[r][1] = v0.y; At[r][2] = v1.x; At[r][3] = v1.y;
+                    Ab[r][0] = v0.x; Ab[r][1] = v0.y; Ab[r][2] = v1.x; Ab[r][3] = v1.y;
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int col = 4 * hi + c;
-                        At[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                        Ab[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
                     }
                 }
             }
-            // register k <- tile column R^k
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                cswap(g16 & 4, At[r][0], At[r][1]);
-                cswap(g16 & 4, At[r][2], At[r][3]);
-                cswap(g16 & 8, At[r][0], At[r][2]);
-                cswap(g16 & 8, At[r][1], At[r][3]);
+            for (int r = 0; r < TG; ++r) {
+                cswap(sw_lo, Ab[r][0], Ab[r][1]);
+                cswap(sw_lo, Ab[r][2], Ab[r][3]);
+                cswap(sw_hi, Ab[r][0], Ab[r][2]);
+                cswap(sw_hi, Ab[r][1], Ab[r][3]);
             }
         }
 
@@ -425,7 +468,7 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
 
             if (a.reduce == VA_REDUCE_NONE) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < TG; ++r)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) Abar[r][c] = 0.0;
                 rbar = 0.0;
@@ -450,11 +493,10 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                 W[0] = lam;
 #pragma unroll
                 for (int m = 1; m <= SADJ; ++m) W[m] = Tab::b(m - 1) != 0.0 ? (a.coef.b[m - 1] * dt_s) * lam : 0.0;
+                // v = w_m o X_{m-1} for the stage about to be processed; later stages get it from the previous one
+                double v = W[SADJ] * blk[HDR + (SADJ - 1) * NP + own];
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
-                    const double Xo = blk[HDR + (m - 1) * NP + own];
-                    const double go = blk[HDR + (SADJ + m - 1) * NP + own];
-                    const double v = W[m] * Xo;
                     double *vb = xs[m & 1];
                     if (writer) vb[own] = v;
                     __syncthreads();
@@ -463,25 +505,47 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
                         mbar_expect_tx(&mbar[bufi ^ 1], BLK * 8);
                         bulk_g2s(xg[bufi ^ 1], slab + (int64_t)(step - 1) * BLK, BLK * 8, &mbar[bufi ^ 1]);
                     }
-                    const double2 *vv2 = reinterpret_cast<const double2 *>(vb + 2 * g16);
+                    const double2 *vv2 = reinterpret_cast<const double2 *>(vb) + g;
                     const double2 *xx2 = reinterpret_cast<const double2 *>(blk + HDR + (m - 1) * NP + 4 * hi);
-                    const double2 v01 = vv2[0], v23 = vv2[16], x01 = xx2[0], x23 = xx2[1];
-                    const double vr[4] = {v01.x, v01.y, v23.x, v23.y};
+                    double vr[TG];
+#pragma unroll
+                    for (int j = 0; j < TG / 2; ++j) {
+                        const double2 q = vv2[LG * j];
+                        vr[2 * j] = q.x;
+                        vr[2 * j + 1] = q.y;
+                    }
+                    const double2 x01 = xx2[0], x23 = xx2[1];
                     const double xc[4] = {x01.x, x01.y, x23.x, x23.y};
                     double s[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) s[c] = fma(At[3][c], vr[3], fma(At[2][c], vr[2], fma(At[1][c], vr[1], At[0][c] * vr[0])));
+                    for (int c = 0; c < 4; ++c) s[c] = Ab[0][c] * vr[0];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                    for (int r = 1; r < TG; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s[c] = fma(Ab[r][c], vr[r], s[c]);
+#pragma unroll
+                    for (int r = 0; r < TG; ++r)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) Abar[r][c] = fma(vr[r], xc[c], Abar[r][c]);
-                    const double sum = reduce16(s[0], s[1], s[2], s[3]); // (A^T v)_own
-                    const double gx = fma(W[m], go, sum);
+                    // gx = (A^T v)_own + w_m g_{m-1}. The next stage's v = (w_{m-1} + gx a dt) X_{m-2} is arranged as
+                    // fma(sum, c1, c2) with c1, c2 known before the reduction returns: one DFMA on the critical path.
+                    const double wg = W[m] * blk[HDR + (SADJ + m - 1) * NP + own];
+                    double c1 = 0.0, c2 = 0.0;
+                    if (m > 1) {
+                        const double Xn = blk[HDR + (m - 2) * NP + own];
+                        if (Tab::a(m - 1, m - 2) != 0.0) c1 = (a.coef.a[m - 1][m - 2] * dt_s) * Xn;
+                        c2 = fma(wg, c1, W[m - 1] * Xn);
+                    }
+                    const double sum = reduce_group<LG>(s[0], s[1], s[2], s[3]);
+                    const double v_next = fma(sum, c1, c2);
+                    const double gx = sum + wg;
+                    const double gxd = gx * dt_s;
                     rbar += v;
                     W[0] += gx;
 #pragma unroll
                     for (int k = 1; k < m; ++k)
-                        if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gx * a.coef.a[m - 1][k - 1], dt_s, W[k]);
+                        if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gxd, a.coef.a[m - 1][k - 1], W[k]);
+                    v = v_next;
                 }
                 lam = W[0];
             }
@@ -489,8 +553,8 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
             if (a.reduce == VA_REDUCE_NONE) {
                 if (writer && own < n) mu_o[own] = rbar;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int row = 2 * g16 + (r & 1) + 32 * (r >> 1);
+                for (int r = 0; r < TG; ++r) {
+                    const int row = FG(r);
                     if (EXACT64) {
                         double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP + 4 * hi);
                         dst[0] = make_double2(Abar[r][0], Abar[r][1]);
@@ -512,8 +576,8 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
         double *part = a.partial + (int64_t)blockIdx.x * npar;
         if (writer && own < n) part[own] = rbar;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int row = 2 * g16 + (r & 1) + 32 * (r >> 1);
+        for (int r = 0; r < TG; ++r) {
+            const int row = FG(r);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int col = 4 * hi + c;
@@ -522,6 +586,8 @@ __global__ void __launch_bounds__(NT, 2) k_glv_wide(const __grid_constant__ VaGl
         }
     }
 }
+
+constexpr int kLG = VA_GLV_LG; // lanes per reduction group, chosen at build time (csrc/Makefile)
 
 template <class Tab, bool ADAPTIVE>
 cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
@@ -534,16 +600,16 @@ cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
         a.coef.b[m] = Tab::b(m);
         a.coef.db[m] = Tab::db(m);
     }
-    if (a.n == NP) k_glv_wide<Tab, ADAPTIVE, true><<<a.grid, NT, 0, st>>>(a);
-    else k_glv_wide<Tab, ADAPTIVE, false><<<a.grid, NT, 0, st>>>(a);
+    if (a.n == NP) k_glv_wide<Tab, ADAPTIVE, true, kLG><<<a.grid, 16 * kLG, 0, st>>>(a);
+    else k_glv_wide<Tab, ADAPTIVE, false, kLG><<<a.grid, 16 * kLG, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 template <class Tab, bool ADAPTIVE>
 cudaError_t occupancy(int n, int *ctas_per_sm)
 {
-    if (n == NP) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, true>, NT, 0);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, false>, NT, 0);
+    if (n == NP) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, true, kLG>, 16 * kLG, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, false, kLG>, 16 * kLG, 0);
 }
 
 int block_of(int stepper)
@@ -590,7 +656,7 @@ cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *c
     if (occ < 1) occ = 1;
     *ctas_per_sm = occ;
     *grid = sms * occ;
-    *threads = NT;
+    *threads = 16 * kLG;
     return cudaSuccess;
 }
 
