@@ -282,13 +282,16 @@ __global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__
                 xc[2 * j] = v.x;
                 xc[2 * j + 1] = v.y;
             }
-            double s[4];
+            // 8 independent accumulator chains (two per tile row) keep the FP64 pipe busy from a single warp
+            double s[4], u[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) s[r] = Af[r][0] * xc[0];
+            for (int r = 0; r < 4; ++r) { s[r] = Af[r][0] * xc[0]; u[r] = Af[r][TG / 2] * xc[TG / 2]; }
 #pragma unroll
-            for (int c = 1; c < TG; ++c)
+            for (int c = 1; c < TG / 2; ++c)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) s[r] = fma(Af[r][c], xc[c], s[r]);
+                for (int r = 0; r < 4; ++r) { s[r] = fma(Af[r][c], xc[c], s[r]); u[r] = fma(Af[r][TG / 2 + c], xc[TG / 2 + c], u[r]); }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s[r] += u[r];
             extra();
             return reduce_group<LG>(s[0], s[1], s[2], s[3]);
         };
@@ -300,11 +303,11 @@ __global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__
         double g0 = r_own + matvec(x, 0, [] {});
         K[0] = x * g0;
 
+        double *sp = slab + HDR + own; // this lane's column in the current step block (advanced on acceptance)
         auto store_stage = [&](int m, double X, double gg) {
             if (writer) {
-                double *blk = slab + (int64_t)nck * BLK + HDR;
-                blk[m * NP + own] = X;
-                blk[(SADJ + m) * NP + own] = gg;
+                sp[m * NP] = X;
+                sp[(SADJ + m) * NP] = gg;
             }
         };
 
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__
             if (fresh) {
                 if (nck >= cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
                 store_stage(0, x, g0);
-                if (tid == 0) slab[(int64_t)nck * BLK] = t;
+                if (tid == 0) sp[-HDR] = t; // own == 0 for thread 0: header of the current block
                 if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
                 trials = 0;
                 fresh = false;
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__
             } else {
                 x = xnew;
                 ++nck;
+                sp += BLK;
                 if (ADAPTIVE) {
                     t += dt;
                     // default_step_adjuster::increase_step
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__
             }
         }
         const int T = nck;
-        if (tid == 0) slab[(int64_t)T * BLK] = t; // header of block T carries the final time
+        if (tid == 0) sp[-HDR] = t; // header of block T carries the final time
         if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
         fence_proxy_async();               // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
         status = __syncthreads_or(status);
@@ -516,13 +520,15 @@ __global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__
                     }
                     const double2 x01 = xx2[0], x23 = xx2[1];
                     const double xc[4] = {x01.x, x01.y, x23.x, x23.y};
-                    double s[4];
+                    double s[4], u[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) s[c] = Ab[0][c] * vr[0];
+                    for (int c = 0; c < 4; ++c) { s[c] = Ab[0][c] * vr[0]; u[c] = Ab[TG / 2][c] * vr[TG / 2]; }
 #pragma unroll
-                    for (int r = 1; r < TG; ++r)
+                    for (int r = 1; r < TG / 2; ++r)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) s[c] = fma(Ab[r][c], vr[r], s[c]);
+                        for (int c = 0; c < 4; ++c) { s[c] = fma(Ab[r][c], vr[r], s[c]); u[c] = fma(Ab[TG / 2 + r][c], vr[TG / 2 + r], u[c]); }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[c] += u[c];
 #pragma unroll
                     for (int r = 0; r < TG; ++r)
 #pragma unroll
