@@ -13,6 +13,7 @@
 //          :160-229 (one-step adjoint), :256-278 (loop over accepted steps), :280-348 (seeds -> lambda, mu).
 //          The AADC vector-Jacobian product (lib/include/AadData.hpp:332-373) is a hand-written device functor.
 #include "va_common.cuh"
+#include "va_pow.h" // glibc-exact pow(): the step-size controller must reproduce the reference bit for bit
 
 namespace {
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(128) k_scalar_forward(const __grid_constant__ 
             }
             if (err > 1.0) {
                 // default_step_adjuster::decrease_step
-                dt *= fmax(0.9 * pow(err, -1.0 / ((double)tab.error_order - 1.0)), 0.2);
+                dt *= fmax(0.9 * va_pow(err, -1.0 / ((double)tab.error_order - 1.0)), 0.2);
                 ++rejects;
                 if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; } // failed_step_checker
             } else {
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(128) k_scalar_forward(const __grid_constant__ 
                 }
                 // default_step_adjuster::increase_step
                 if (err < 0.5) {
-                    err = fmax(pow(5.0, -(double)tab.stepper_order), err);
-                    dt *= 9.0 / 10.0 * pow(err, -1.0 / (double)tab.stepper_order);
+                    err = fmax(va_pow(5.0, -(double)tab.stepper_order), err);
+                    dt *= 9.0 / 10.0 * va_pow(err, -1.0 / (double)tab.stepper_order);
                 }
                 ++count;
                 fresh = true;
