@@ -72,12 +72,19 @@ def cpu_run(sample, threads):
     return dt, kind
 
 
+def _calibrate(cores):
+    """gradients/s of the CPU path from two short runs; the difference cancels the one-off cost (AADC records and
+    JIT-compiles the RHS once per thread, ~0.2 s at N=64)."""
+    t1, _ = cpu_run(2 * cores, cores)
+    t2, _ = cpu_run(6 * cores, cores)
+    return 4 * cores / max(t2 - t1, 1e-3)
+
+
 def cpu_baseline(sample=0):
     cores = os.cpu_count() or 1
     if sample <= 0:
-        t, _ = cpu_run(4 * cores, cores)  # calibration (includes the one-off AADC recording per thread)
-        rate = 4 * cores / max(t, 1e-3)
-        sample = int(max(8 * cores, min(65536, rate * 12)))  # ~12 s of CPU work
+        rate = _calibrate(cores)
+        sample = int(max(8 * cores, min(65536, rate * 15)))  # ~15 s of CPU work
         sample -= sample % cores
     t, kind = cpu_run(sample, cores)
     return dict(value=sample / t, unit="gradients/s", cores=cores, kind=kind,
@@ -92,9 +99,8 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     sample = args.cpu_sample
     if sample <= 0:
-        t, _ = cpu_run(4 * cores, cores)
-        rate = 4 * cores / max(t, 1e-3)
-        sample = int(max(8 * cores, min(32768, rate * 8)))
+        rate = _calibrate(cores)
+        sample = int(max(8 * cores, min(32768, rate * 8)))  # ~8 s per step
         sample -= sample % cores
     for _ in range(args.warmup):
         cpu_run(max(cores, sample // 8), cores)
@@ -115,6 +121,17 @@ def reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per full-size launch, from the committed
+    ncu --set full capture (profiles/r01_traffic.json); None when no capture has been recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def workload_config(args, extra=None):
@@ -278,7 +295,7 @@ def main():
         alg_bytes = Bl * (8 * NPAR + 8 * N * 3) + (0 if red == va.REDUCE_SUM else Bl * 8 * NPAR)
         line["roofline"] = {
             "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-            "traffic": None,
+            "traffic": _ncu_traffic(),
             "peak_source": "DFMA microbenchmark run live on this GPU (va_measure_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
             "kernel": "k_glv_wide<TabCK54,adaptive,N=64> (one launch per step per GPU; + a 296-row reduction kernel)",
             "kernel_ms": kernel_ms, "flops_per_launch": flops_exec, "flops_counting": "executed algorithmic FP64 flops of rank 0: "
