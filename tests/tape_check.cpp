@@ -1,0 +1,94 @@
+// CPU check of the tape recorder behind recordDriverRHSFunction (vectorizedadjoint_b200/include/va_tape.hpp).
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+
+#include "lib.hpp"
+
+struct HO {
+    double k = 1.0;
+    template <class T> void operator()(const std::vector<T> &r, std::vector<T> &d, const std::vector<T> &mu, const T) const
+    {
+        d[0] = r[1];
+        d[1] = -k * r[0] - mu[0] * r[1];
+    }
+};
+struct HO_k2 { // same structure, different constant: must NOT be taken for the built-in functor
+    double k = 2.0;
+    template <class T> void operator()(const std::vector<T> &r, std::vector<T> &d, const std::vector<T> &mu, const T) const
+    {
+        d[0] = r[1];
+        d[1] = -k * r[0] - mu[0] * r[1];
+    }
+};
+struct VdP {
+    template <class T> void operator()(const std::vector<T> &x, std::vector<T> &d, const std::vector<T> &mu, const T) const
+    {
+        d[0] = x[1];
+        d[1] = mu[0] * ((1.0 - x[0] * x[0]) * x[1] - x[0]);
+    }
+};
+struct GLV {
+    template <class T> void operator()(const std::vector<T> &x, std::vector<T> &d, const std::vector<T> &p, T)
+    {
+        int N = x.size();
+        for (int i = 0; i < N; i++) {
+            T sum = 0.0;
+            for (int j = 0; j < N; j++) sum += p[N * (i + 1) + j] * x[j];
+            d[i] = x[i] * (p[i] + sum);
+        }
+    }
+};
+struct GLV_reordered { // mathematically the same RHS written differently: still the built-in functor
+    template <class T> void operator()(const std::vector<T> &x, std::vector<T> &d, const std::vector<T> &p, T)
+    {
+        int N = x.size();
+        for (int i = 0; i < N; i++) {
+            T acc = p[i] * x[i];
+            for (int j = N - 1; j >= 0; j--) acc += x[i] * x[j] * p[N * (i + 1) + j];
+            d[i] = acc;
+        }
+    }
+};
+struct Pendulum {
+    template <class T> void operator()(const std::vector<T> &x, std::vector<T> &d, const std::vector<T> &p, const T t) const
+    {
+        using std::sin;
+        d[0] = x[1];
+        d[1] = -p[0] * sin(x[0]) - p[1] * x[1] + exp(-t) / (1.0 + x[0] * x[0]);
+    }
+};
+
+int main()
+{
+    int fails = 0;
+    auto expect = [&](const char *name, int got, int want) {
+        std::printf("%-16s kind %d (want %d)\n", name, got, want);
+        fails += got != want;
+    };
+    expect("harmonic", va::identify(va::record(HO(), 2, 1)), va::SYS_HARMONIC);
+    expect("harmonic k=2", va::identify(va::record(HO_k2(), 2, 1)), va::SYS_TAPE);
+    expect("vanderpol", va::identify(va::record(VdP(), 2, 1)), va::SYS_VANDERPOL);
+    expect("glv N=5", va::identify(va::record(GLV(), 5, 30)), va::SYS_GLV);
+    expect("glv N=64", va::identify(va::record(GLV(), 64, 4160)), va::SYS_GLV);
+    expect("glv reordered", va::identify(va::record(GLV_reordered(), 7, 56)), va::SYS_GLV);
+    expect("pendulum", va::identify(va::record(Pendulum(), 2, 2)), va::SYS_TAPE);
+    // tape evaluation == direct evaluation; generated vjp source is straight-line CUDA
+    va::Tape tp = va::record(Pendulum(), 2, 2);
+    std::vector<double> x = {0.4, -0.2}, p = {1.3, 0.05}, f(2), g(2), work;
+    tp.eval(x.data(), p.data(), 0.7, f.data(), work);
+    Pendulum()(x, g, p, 0.7);
+    fails += !(f[0] == g[0] && std::fabs(f[1] - g[1]) < 1e-15);
+    const std::string src = tp.cuda_source("SysPendulum");
+    fails += src.find("__device__ static void vjp") == std::string::npos || src.find("sin(") == std::string::npos;
+    // Driver surface without a device: preconditions are reported on stdout, the call returns (reference behaviour)
+    vectorizedadjoint::Driver driver(2, 1, 1);
+    std::vector<double> mu = {0.1};
+    vectorizedadjoint::adjointSolve(driver, mu); // prints "Must call setCostGradients() first!"
+    vectorizedadjoint::recordDriverRHSFunction(driver, HO());
+    std::vector<double> u = {0.5, 0.25}, du(2);
+    driver.Rhs(u, du, mu, 0.0);
+    fails += !(du[0] == 0.25 && std::fabs(du[1] - (-0.5 - 0.1 * 0.25)) < 1e-16);
+    std::printf("%s\n", fails ? "FAILED" : "tape ok");
+    return fails;
+}

@@ -1,0 +1,296 @@
+// va_tape.hpp -- records the user's templated right-hand-side functor on an active scalar type.
+//
+// Replaces the recording half of the reference's AadData (lib/include/AadData.hpp:124-171: AADC idouble, startRecording /
+// markAsInput / markAsOutput / stopRecording). The hook is the same: the system functor is a template on the scalar type
+//     template <class T> void operator()(const std::vector<T>& x, std::vector<T>& dxdt, const std::vector<T>& p, const T t)
+// (reference doc/source/harmonicOscillator.rst:85). Calling it once with va::adouble yields a straight-line tape of the
+// RHS. The tape is used to (1) evaluate f on the host (Driver::Rhs), (2) identify the system: if the tape computes
+// one of the engine's built-in device functors (harmonic oscillator, Van der Pol, generalized Lotka-Volterra) the
+// hand-written sm_100a kernels are selected; (3) emit CUDA source for rhs / vjp device functors (tape -> CUDA).
+#ifndef VA_B200_TAPE_HPP
+#define VA_B200_TAPE_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace va {
+
+enum OpCode : uint8_t { OP_INPUT_X, OP_INPUT_P, OP_INPUT_T, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP,
+                        OP_LOG, OP_SQRT, OP_TANH, OP_POW };
+
+struct Node {
+    OpCode op;
+    int32_t a, b;   // operand node ids (or input index for OP_INPUT_*)
+    double c;       // constant value (OP_CONST)
+};
+
+class Tape
+{
+  public:
+    std::vector<Node> nodes;
+    std::vector<int32_t> outputs; // node id of dxdt[i]
+    int n_x = 0, n_p = 0;
+
+    int32_t push(OpCode op, int32_t a = -1, int32_t b = -1, double c = 0.0)
+    {
+        nodes.push_back(Node{op, a, b, c});
+        return static_cast<int32_t>(nodes.size()) - 1;
+    }
+
+    // f(x, p, t) on the host
+    void eval(const double *x, const double *p, double t, double *dxdt, std::vector<double> &work) const
+    {
+        work.resize(nodes.size());
+        for (size_t k = 0; k < nodes.size(); ++k) {
+            const Node &n = nodes[k];
+            double v = 0.0;
+            switch (n.op) {
+            case OP_INPUT_X: v = x[n.a]; break;
+            case OP_INPUT_P: v = p[n.a]; break;
+            case OP_INPUT_T: v = t; break;
+            case OP_CONST: v = n.c; break;
+            case OP_ADD: v = work[n.a] + work[n.b]; break;
+            case OP_SUB: v = work[n.a] - work[n.b]; break;
+            case OP_MUL: v = work[n.a] * work[n.b]; break;
+            case OP_DIV: v = work[n.a] / work[n.b]; break;
+            case OP_NEG: v = -work[n.a]; break;
+            case OP_SIN: v = std::sin(work[n.a]); break;
+            case OP_COS: v = std::cos(work[n.a]); break;
+            case OP_EXP: v = std::exp(work[n.a]); break;
+            case OP_LOG: v = std::log(work[n.a]); break;
+            case OP_SQRT: v = std::sqrt(work[n.a]); break;
+            case OP_TANH: v = std::tanh(work[n.a]); break;
+            case OP_POW: v = std::pow(work[n.a], work[n.b]); break;
+            }
+            work[k] = v;
+        }
+        for (size_t i = 0; i < outputs.size(); ++i) dxdt[i] = work[outputs[i]];
+    }
+
+    // CUDA source of the device functors: straight-line rhs and reverse-mode vjp (tape -> CUDA generator).
+    std::string cuda_source(const std::string &name) const;
+};
+
+inline Tape *&active_tape()
+{
+    static thread_local Tape *t = nullptr;
+    return t;
+}
+
+// Active scalar. Outside a recording it behaves like a plain double (node == -1).
+class adouble
+{
+  public:
+    double val = 0.0;
+    int32_t node = -1;
+
+    adouble() = default;
+    adouble(double v) : val(v) {}
+    adouble(int v) : val(v) {}
+
+    int32_t id() const
+    {
+        if (node >= 0) return node;
+        Tape *t = active_tape();
+        if (!t) throw std::logic_error("va::adouble used in an expression outside a recording");
+        return t->push(OP_CONST, -1, -1, val);
+    }
+    static adouble make(OpCode op, double v, int32_t a, int32_t b = -1)
+    {
+        adouble r;
+        r.val = v;
+        r.node = active_tape()->push(op, a, b);
+        return r;
+    }
+    static bool rec(const adouble &a, const adouble &b) { return active_tape() && (a.node >= 0 || b.node >= 0); }
+    static bool rec(const adouble &a) { return active_tape() && a.node >= 0; }
+
+    adouble &operator+=(const adouble &o) { return *this = *this + o; }
+    adouble &operator-=(const adouble &o) { return *this = *this - o; }
+    adouble &operator*=(const adouble &o) { return *this = *this * o; }
+    adouble &operator/=(const adouble &o) { return *this = *this / o; }
+
+    friend adouble operator+(const adouble &a, const adouble &b)
+    {
+        return rec(a, b) ? make(OP_ADD, a.val + b.val, a.id(), b.id()) : adouble(a.val + b.val);
+    }
+    friend adouble operator-(const adouble &a, const adouble &b)
+    {
+        return rec(a, b) ? make(OP_SUB, a.val - b.val, a.id(), b.id()) : adouble(a.val - b.val);
+    }
+    friend adouble operator*(const adouble &a, const adouble &b)
+    {
+        return rec(a, b) ? make(OP_MUL, a.val * b.val, a.id(), b.id()) : adouble(a.val * b.val);
+    }
+    friend adouble operator/(const adouble &a, const adouble &b)
+    {
+        return rec(a, b) ? make(OP_DIV, a.val / b.val, a.id(), b.id()) : adouble(a.val / b.val);
+    }
+    friend adouble operator-(const adouble &a) { return rec(a) ? make(OP_NEG, -a.val, a.id()) : adouble(-a.val); }
+    friend adouble operator+(const adouble &a) { return a; }
+};
+
+#define VA_TAPE_UNARY(FN, OP)                                                                      \
+    inline adouble FN(const adouble &a)                                                            \
+    {                                                                                              \
+        return adouble::rec(a) ? adouble::make(OP, std::FN(a.val), a.id()) : adouble(std::FN(a.val)); \
+    }
+VA_TAPE_UNARY(sin, OP_SIN)
+VA_TAPE_UNARY(cos, OP_COS)
+VA_TAPE_UNARY(exp, OP_EXP)
+VA_TAPE_UNARY(log, OP_LOG)
+VA_TAPE_UNARY(sqrt, OP_SQRT)
+VA_TAPE_UNARY(tanh, OP_TANH)
+#undef VA_TAPE_UNARY
+inline adouble pow(const adouble &a, const adouble &b)
+{
+    return adouble::rec(a, b) ? adouble::make(OP_POW, std::pow(a.val, b.val), a.id(), b.id()) : adouble(std::pow(a.val, b.val));
+}
+
+// Record system(x, dxdt, p, t) once. Mirrors AadData::Record (reference lib/include/AadData.hpp:124-171).
+template <class System>
+Tape record(System system, int n_x, int n_p)
+{
+    Tape tape;
+    tape.n_x = n_x;
+    tape.n_p = n_p;
+    Tape *prev = active_tape();
+    active_tape() = &tape;
+    try {
+        std::vector<adouble> x(n_x), p(n_p), f(n_x);
+        adouble t;
+        for (int i = 0; i < n_x; ++i) { x[i].val = 0.3 + 0.01 * i; x[i].node = tape.push(OP_INPUT_X, i); }
+        for (int k = 0; k < n_p; ++k) { p[k].val = 1.0; p[k].node = tape.push(OP_INPUT_P, k); }
+        t.node = tape.push(OP_INPUT_T);
+        system(x, f, p, t);
+        tape.outputs.resize(n_x);
+        for (int i = 0; i < n_x; ++i) tape.outputs[i] = f[i].id();
+    } catch (...) {
+        active_tape() = prev;
+        throw;
+    }
+    active_tape() = prev;
+    return tape;
+}
+
+// ---- built-in systems the engine has hand-written device functors for -----------------------------------------------
+enum SystemKind { SYS_HARMONIC = 0, SYS_VANDERPOL = 1, SYS_GLV = 2, SYS_TAPE = 3 };
+
+inline void builtin_rhs(int kind, int n, const double *x, const double *p, double *f)
+{
+    if (kind == SYS_HARMONIC) {
+        f[0] = x[1];
+        f[1] = -1.0 * x[0] - p[0] * x[1];
+    } else if (kind == SYS_VANDERPOL) {
+        f[0] = x[1];
+        f[1] = p[0] * ((1.0 - x[0] * x[0]) * x[1] - x[0]);
+    } else {
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s += p[n * (i + 1) + j] * x[j];
+            f[i] = x[i] * (p[i] + s);
+        }
+    }
+}
+
+// Which built-in functor does the tape compute? Decided numerically: the tape is evaluated at a few pseudo-random
+// points and compared with the built-in formulas (robust against a different operation order in the user's functor).
+inline int identify(const Tape &tape)
+{
+    const int n = tape.n_x, np = tape.n_p;
+    std::vector<int> candidates;
+    if (n == 2 && np == 1) { candidates.push_back(SYS_HARMONIC); candidates.push_back(SYS_VANDERPOL); }
+    if (np == n * n + n) candidates.push_back(SYS_GLV);
+    std::vector<double> x(n), p(np), f(n), g(n), work;
+    for (int kind : candidates) {
+        bool same = true;
+        uint64_t s = 0x243F6A8885A308D3ULL;
+        for (int trial = 0; trial < 3 && same; ++trial) {
+            auto u = [&]() { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(s >> 11) * 0x1.0p-53 * 2.0 - 1.0; };
+            for (auto &v : x) v = u();
+            for (auto &v : p) v = 2.0 * u();
+            tape.eval(x.data(), p.data(), 0.37 * trial, f.data(), work);
+            builtin_rhs(kind, n, x.data(), p.data(), g.data());
+            for (int i = 0; i < n; ++i) same = same && std::fabs(f[i] - g[i]) <= 1e-12 * (1.0 + std::fabs(g[i]));
+        }
+        if (same) return kind;
+    }
+    return SYS_TAPE;
+}
+
+// ---- tape -> CUDA ----------------------------------------------------------------------------------------------------
+inline std::string Tape::cuda_source(const std::string &name) const
+{
+    std::ostringstream o;
+    o.precision(17);
+    auto v = [](int32_t k) { return "v" + std::to_string(k); };
+    auto d = [](int32_t k) { return "d" + std::to_string(k); };
+    o << "// generated by va::Tape::cuda_source -- rhs and vjp of a recorded system (" << nodes.size() << " nodes)\n";
+    o << "struct " << name << " {\n  static constexpr int N = " << n_x << ", NPAR = " << n_p << ";\n";
+    auto forward = [&]() {
+        for (size_t k = 0; k < nodes.size(); ++k) {
+            const Node &n = nodes[k];
+            o << "    const double " << v((int32_t)k) << " = ";
+            switch (n.op) {
+            case OP_INPUT_X: o << "x[" << n.a << "]"; break;
+            case OP_INPUT_P: o << "p[" << n.a << "]"; break;
+            case OP_INPUT_T: o << "t"; break;
+            case OP_CONST: o << std::hexfloat << n.c << std::defaultfloat; break;
+            case OP_ADD: o << v(n.a) << " + " << v(n.b); break;
+            case OP_SUB: o << v(n.a) << " - " << v(n.b); break;
+            case OP_MUL: o << v(n.a) << " * " << v(n.b); break;
+            case OP_DIV: o << v(n.a) << " / " << v(n.b); break;
+            case OP_NEG: o << "-" << v(n.a); break;
+            case OP_SIN: o << "sin(" << v(n.a) << ")"; break;
+            case OP_COS: o << "cos(" << v(n.a) << ")"; break;
+            case OP_EXP: o << "exp(" << v(n.a) << ")"; break;
+            case OP_LOG: o << "log(" << v(n.a) << ")"; break;
+            case OP_SQRT: o << "sqrt(" << v(n.a) << ")"; break;
+            case OP_TANH: o << "tanh(" << v(n.a) << ")"; break;
+            case OP_POW: o << "pow(" << v(n.a) << ", " << v(n.b) << ")"; break;
+            }
+            o << ";\n";
+        }
+    };
+    o << "  __device__ static void rhs(const double *x, const double *p, double t, double *dx) {\n";
+    forward();
+    for (size_t i = 0; i < outputs.size(); ++i) o << "    dx[" << i << "] = " << v(outputs[i]) << ";\n";
+    o << "  }\n";
+    o << "  __device__ static void vjp(const double *x, const double *p, double t, const double *w, double *gx, double *gp) {\n";
+    forward();
+    for (size_t k = 0; k < nodes.size(); ++k) o << "    double " << d((int32_t)k) << " = 0.0;\n";
+    for (size_t i = 0; i < outputs.size(); ++i) o << "    " << d(outputs[i]) << " += w[" << i << "];\n";
+    for (int32_t k = (int32_t)nodes.size() - 1; k >= 0; --k) {
+        const Node &n = nodes[k];
+        switch (n.op) {
+        case OP_ADD: o << "    " << d(n.a) << " += " << d(k) << "; " << d(n.b) << " += " << d(k) << ";\n"; break;
+        case OP_SUB: o << "    " << d(n.a) << " += " << d(k) << "; " << d(n.b) << " -= " << d(k) << ";\n"; break;
+        case OP_MUL: o << "    " << d(n.a) << " += " << d(k) << " * " << v(n.b) << "; " << d(n.b) << " += " << d(k) << " * " << v(n.a) << ";\n"; break;
+        case OP_DIV: o << "    " << d(n.a) << " += " << d(k) << " / " << v(n.b) << "; " << d(n.b) << " -= " << d(k) << " * " << v(k) << " / " << v(n.b) << ";\n"; break;
+        case OP_NEG: o << "    " << d(n.a) << " -= " << d(k) << ";\n"; break;
+        case OP_SIN: o << "    " << d(n.a) << " += " << d(k) << " * cos(" << v(n.a) << ");\n"; break;
+        case OP_COS: o << "    " << d(n.a) << " -= " << d(k) << " * sin(" << v(n.a) << ");\n"; break;
+        case OP_EXP: o << "    " << d(n.a) << " += " << d(k) << " * " << v(k) << ";\n"; break;
+        case OP_LOG: o << "    " << d(n.a) << " += " << d(k) << " / " << v(n.a) << ";\n"; break;
+        case OP_SQRT: o << "    " << d(n.a) << " += " << d(k) << " * 0.5 / " << v(k) << ";\n"; break;
+        case OP_TANH: o << "    " << d(n.a) << " += " << d(k) << " * (1.0 - " << v(k) << " * " << v(k) << ");\n"; break;
+        case OP_POW:
+            o << "    " << d(n.a) << " += " << d(k) << " * " << v(n.b) << " * pow(" << v(n.a) << ", " << v(n.b) << " - 1.0); " << d(n.b)
+              << " += " << d(k) << " * " << v(k) << " * log(" << v(n.a) << ");\n";
+            break;
+        case OP_INPUT_X: o << "    gx[" << n.a << "] = " << d(k) << ";\n"; break;
+        case OP_INPUT_P: o << "    gp[" << n.a << "] += " << d(k) << ";\n"; break;
+        default: break;
+        }
+    }
+    o << "  }\n};\n";
+    return o.str();
+}
+
+} // namespace va
+
+#endif
