@@ -216,8 +216,7 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
 
     N, B = N_SPECIES, args.batch
-    Bl = B // world + (1 if rank < B % world else 0)
-    b0 = rank * (B // world) + min(rank, B % world)
+    b0, Bl = va.shard_range(B, rank, world)
     red = va.REDUCE_SUM if args.reduce == "sum" else va.REDUCE_NONE
     f64 = dict(dtype=torch.float64, device=dev)
 

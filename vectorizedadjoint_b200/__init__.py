@@ -21,7 +21,7 @@ import numpy as np
 
 __all__ = ["Engine", "EngineError", "lib", "build", "SYS_HARMONIC", "SYS_VANDERPOL", "SYS_GLV", "RK_EULER", "RK_RK4", "RK_CK54",
            "RK_DOPRI5", "RK_RKF78", "OBJ_SEED", "OBJ_SUM", "OBJ_HALF_NORM2", "REDUCE_NONE", "REDUCE_SUM", "synth_batch_device",
-           "measure_fp64_peak", "measure_hbm_copy", "npar_of"]
+           "measure_fp64_peak", "measure_hbm_copy", "npar_of", "shard_range"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libva_engine.so")
@@ -103,6 +103,15 @@ def lib():
 def _check(rc: int, what: str):
     if rc != 0:
         raise EngineError(f"{what} failed ({rc}): {lib().va_last_error().decode()}")
+
+
+def shard_range(batch: int, rank: int, world: int):
+    """Contiguous shard [b0, b0 + count) of a batch of parameter sets for `rank` of `world` (the only multi-GPU
+    decomposition on this path: independent trajectories, no data-path collective)."""
+    base, rem = divmod(batch, world)
+    count = base + (1 if rank < rem else 0)
+    b0 = rank * base + min(rank, rem)
+    return b0, count
 
 
 def npar_of(system: int, n: int) -> int:
