@@ -129,9 +129,9 @@ def _ncu_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             d = json.load(f)
-        return d.get("dram_bytes_per_launch")
+        return d.get("dram_bytes_per_launch"), d.get("launch_parameter_sets", 1 << 20)
     except Exception:
-        return None
+        return None, None
 
 
 def workload_config(args, extra=None):
@@ -294,7 +294,7 @@ def main():
         alg_bytes = Bl * (8 * NPAR + 8 * N * 3) + (0 if red == va.REDUCE_SUM else Bl * 8 * NPAR)
         line["roofline"] = {
             "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-            "traffic": _ncu_traffic(),
+            "traffic": (lambda tb: int(tb[0] * Bl / tb[1]) if tb[0] else None)(_ncu_traffic()),
             "peak_source": "DFMA microbenchmark run live on this GPU (va_measure_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
             "kernel": "k_glv_wide<TabCK54,adaptive,N=64> (one launch per step per GPU; + a 296-row reduction kernel)",
             "kernel_ms": kernel_ms, "flops_per_launch": flops_exec, "flops_counting": "executed algorithmic FP64 flops of rank 0: "

@@ -31,10 +31,15 @@
 // Accept/reject logic is odeint's (same error norm, same step-size rules). The matrix-vector products use FMA and a
 // tree reduction, so stage values differ from the scalar reference by round-off; accepted-step counts can therefore
 // flip only when the error estimate is within ~1e-8 relative of a threshold (documented in DESIGN.md).
+#include <cstdlib>
+
 #include "va_common.cuh"
 
 #ifndef VA_GLV_LG
 #define VA_GLV_LG 8
+#endif
+#ifndef VA_GLV_MINB
+#define VA_GLV_MINB 2 // resident CTAs per SM the register allocation is sized for
 #endif
 
 namespace {
@@ -137,6 +142,12 @@ __device__ __forceinline__ double reduce_group(double s0, double s1, double s2, 
 {
     double k0 = s0 + shfl_xor_d(s2, LG / 2);
     const double k1 = s1 + shfl_xor_d(s3, LG / 2);
+    if (LG == 8) {
+        // the last halving step and the last butterfly in ONE exchange round: the three other lanes of the quad hold
+        // this lane's entry in k0 (lane^1) or k1 (lanes ^2, ^3). Symmetric add tree -> lanes g and g^1 agree bit for bit.
+        const double a1 = shfl_xor_d(k0, 1), a2 = shfl_xor_d(k1, 2), a3 = shfl_xor_d(k1, 3);
+        return (k0 + a1) + (a2 + a3);
+    }
     k0 += shfl_xor_d(k1, LG / 4);
 #pragma unroll
     for (int d = LG / 8; d >= 1; d >>= 1) k0 += shfl_xor_d(k0, d);
@@ -186,7 +197,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // LG = lanes per reduction group: 16 -> 256 threads, 4x4 tiles; 8 -> 128 threads, 4x8 / 8x4 tiles (fewer operand and
 // shuffle wavefronts per DFMA, twice the registers per thread).
 template <class Tab, bool ADAPTIVE, bool EXACT64, int LG>
-__global__ void __launch_bounds__(16 * LG, 2) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
+__global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int NT = 16 * LG;      // threads per CTA
     constexpr int TG = NP / LG;      // tile extent along the lane (g) direction: 4 or 8
@@ -660,6 +671,10 @@ cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *c
     }
     if (err != cudaSuccess) return err;
     if (occ < 1) occ = 1;
+    if (const char *env = getenv("VA_GLV_CTAS_PER_SM")) { // experiment knob: fewer resident CTAs than the occupancy limit
+        const int v = atoi(env);
+        if (v >= 1 && v < occ) occ = v;
+    }
     *ctas_per_sm = occ;
     *grid = sms * occ;
     *threads = 16 * kLG;
