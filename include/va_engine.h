@@ -37,7 +37,9 @@
 #ifndef VA_ENGINE_H
 #define VA_ENGINE_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -111,6 +113,7 @@ typedef struct va_engine_info {
     char device_name[64];
 } va_engine_info;
 
+#ifndef __CUDACC_RTC__ /* the enums and structs above are also seen by run-time compiled device code */
 int va_engine_create(const va_engine_desc *desc, va_engine **out);
 void va_engine_destroy(va_engine *e);
 int va_engine_get_info(va_engine *e, va_engine_info *info);
@@ -124,6 +127,11 @@ int va_forward_adjoint_batch(va_engine *e, const va_batch_args *args);
  * Pass t = x = NULL to query the count only. */
 int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, double *x, int32_t *count);
 
+/* VA_SYS_TAPE support: compile (NVRTC, sm_100a) the thread-per-trajectory kernels for the recorded system whose device
+ * functors are given as CUDA source (va::Tape::cuda_source("VaUserSys"), replacing AadData::Record + the AADC JIT,
+ * lib/include/AadData.hpp:124-171). Compile only, no device needed; log receives the compiler output. */
+int va_tape_compile_check(const char *tape_cuda_src, int32_t stepper, char *log, int32_t log_capacity);
+
 /* Synthetic, seeded parameter sets generated on the device (bench inputs; bit-identical to the host generator used
  * by the tests). params_dev [B][n_par], x0_dev [B][n_state]; b0 = global index of the first set (sharding). */
 int va_synth_batch_device(int32_t system, int32_t n_state, uint64_t seed, int64_t b0, int64_t B, double *params_dev,
@@ -132,6 +140,7 @@ int va_synth_batch_device(int32_t system, int32_t n_state, uint64_t seed, int64_
 /* Microbenchmarks for the roofline denominators, measured on the device the call runs on. */
 int va_measure_fp64_peak(int32_t device, double *tflops);
 int va_measure_hbm_copy(int32_t device, double *gbytes_per_s);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,16 @@ int main()
     fails += !(f[0] == g[0] && std::fabs(f[1] - g[1]) < 1e-15);
     const std::string src = tp.cuda_source("SysPendulum");
     fails += src.find("__device__ static void vjp") == std::string::npos || src.find("sin(") == std::string::npos;
+    // tape -> CUDA -> NVRTC (sm_100a): the generated functor compiles inside the engine's thread-per-trajectory kernels,
+    // for a fixed-step and for controlled steppers (no device needed for the compile step)
+    char log[4096];
+    const std::string user = tp.cuda_source("VaUserSys");
+    for (int stepper : {VA_RK_RK4, VA_RK_DOPRI5, VA_RK_RKF78}) {
+        const int rc = va_tape_compile_check(user.c_str(), stepper, log, sizeof(log));
+        std::printf("nvrtc stepper %d: rc %d %s\n", stepper, rc, rc ? va_last_error() : "");
+        fails += rc != VA_OK;
+    }
+    fails += va_tape_compile_check("struct VaUserSys { this is not CUDA };", VA_RK_RK4, log, sizeof(log)) != VA_E_NVRTC;
     // Driver surface without a device: preconditions are reported on stdout, the call returns (reference behaviour)
     vectorizedadjoint::Driver driver(2, 1, 1);
     std::vector<double> mu = {0.1};

@@ -66,3 +66,10 @@ def test_own_lotka_client_full_sensitivity():
     assert "Number of steps: 19" in out or "Number of steps:" in out
     m = re.search(r"sum x\(tf\) = (\S+), sum dx\(tf\)/dx0 = (\S+), sum dx\(tf\)/dalpha = (\S+)", out)
     assert m and all(np.isfinite(float(v)) for v in m.groups())
+
+
+def test_recorded_system_runs_through_tape_to_cuda():
+    """A functor with no built-in device code: tape -> CUDA source -> NVRTC -> thread-per-trajectory kernels; the adjoint
+    matches central finite differences (the program checks it itself)."""
+    out = run("pendulum")
+    assert "pendulum ok" in out, out

@@ -34,7 +34,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 TRAJ_OK, TRAJ_CKPT_OVERFLOW, TRAJ_NO_PROGRESS, TRAJ_NONFINITE = 0, 1, 2, 4
 
 EXPORTS = ["va_engine_create", "va_engine_destroy", "va_engine_get_info", "va_last_error", "va_forward_batch", "va_adjoint_batch",
-           "va_forward_adjoint_batch", "va_get_checkpoints", "va_synth_batch_device", "va_measure_fp64_peak", "va_measure_hbm_copy"]
+           "va_forward_adjoint_batch", "va_get_checkpoints", "va_tape_compile_check", "va_synth_batch_device", "va_measure_fp64_peak", "va_measure_hbm_copy"]
 
 
 class EngineError(RuntimeError):

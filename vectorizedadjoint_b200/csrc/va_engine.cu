@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "va_common.cuh"
+#include "va_jit.h"
 
 namespace {
 
@@ -38,7 +39,7 @@ int fail(int code, const std::string &msg)
                         std::string(#call) + ": " + cudaGetErrorString(err__));                             \
     } while (0)
 
-enum Family { FAM_SCALAR = 0, FAM_GLV_WIDE = 1 };
+enum Family { FAM_SCALAR = 0, FAM_GLV_WIDE = 1, FAM_TAPE = 3 }; // TAPE: scalar kernels compiled at run time for a recorded system
 
 struct DevBuf {
     void *p = nullptr;
@@ -69,6 +70,7 @@ struct va_engine {
     va_engine_desc desc;
     VaTableau tab;
     int family = FAM_SCALAR;
+    VaJitModule *jit = nullptr;
     int device = 0, sm_count = 0;
     int cap = 0;
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
@@ -133,6 +135,26 @@ int ensure_workspace(va_engine *e, int64_t B)
     return VA_OK;
 }
 
+// thread-per-trajectory kernels: ahead-of-time instantiations for the built-in systems, NVRTC module for recorded ones
+int scalar_forward(va_engine *e, const VaScalarArgs &a, cudaStream_t st)
+{
+    if (e->family == FAM_TAPE) {
+        if (int cr = va_jit_launch(e->jit, 0, a, a.B, st)) return fail(VA_E_CUDA, "cuLaunchKernel(forward) failed: " + std::to_string(cr));
+        return VA_OK;
+    }
+    VA_CUDA(va_scalar_forward(a, st));
+    return VA_OK;
+}
+int scalar_adjoint(va_engine *e, const VaScalarArgs &a, cudaStream_t st)
+{
+    if (e->family == FAM_TAPE) {
+        if (int cr = va_jit_launch(e->jit, 1, a, a.B * a.n_out, st)) return fail(VA_E_CUDA, "cuLaunchKernel(adjoint) failed: " + std::to_string(cr));
+        return VA_OK;
+    }
+    VA_CUDA(va_scalar_adjoint(a, st));
+    return VA_OK;
+}
+
 struct DevArgs { // all pointers on the device
     int64_t B;
     const double *x0, *params;
@@ -151,7 +173,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
     if (d.B <= 0) return VA_OK;
     if (int rc = ensure_workspace(e, d.B)) return rc;
     int32_t *acc = d.n_accept, *rej = d.n_reject, *sta = d.status;
-    if (e->family == FAM_SCALAR) { // the reverse kernel needs them
+    if (e->family != FAM_GLV_WIDE) { // the reverse kernel needs them
         if (!acc) { if (int rc = e->own_accept.ensure((size_t)d.B * 4)) return rc; acc = e->own_accept.as<int32_t>(); }
         if (!rej) { if (int rc = e->own_reject.ensure((size_t)d.B * 4)) return rc; rej = e->own_reject.as<int32_t>(); }
         if (!sta) { if (int rc = e->own_status.ensure((size_t)d.B * 4)) return rc; sta = e->own_status.as<int32_t>(); }
@@ -208,10 +230,10 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.mu = sum ? e->mu_tmp.as<double>() : (d.mu ? d.mu + b0 * nout * npar : nullptr);
         a.n_accept = acc + b0; a.n_reject = rej + b0; a.status = sta + b0;
         a.ck_t = e->ck_t.as<double>(); a.ck_x = e->ck_x.as<double>();
-        VA_CUDA(va_scalar_forward(a, st));
+        if (int rc = scalar_forward(e, a, st)) return rc;
         ++e->launches;
         if (d.forward_only) continue;
-        VA_CUDA(va_scalar_adjoint(a, st));
+        if (int rc = scalar_adjoint(e, a, st)) return rc;
         ++e->launches;
         if (sum) {
             VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), Bw, (int64_t)nout * npar, (int64_t)nout * npar, d.mu,
@@ -367,6 +389,12 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
             return fail(VA_E_UNSUPPORTED, "GLV: supported are N <= 64 with rk4 (fixed step), cash_karp54 or dopri5 (controlled)");
         family = FAM_GLV_WIDE;
         break;
+    case VA_SYS_TAPE:
+        if (!desc->tape_cuda_src) return fail(VA_E_INVALID, "VA_SYS_TAPE needs tape_cuda_src (va::Tape::cuda_source(\"VaUserSys\"))");
+        if (desc->n_state > 16 || desc->n_par > 256)
+            return fail(VA_E_UNSUPPORTED, "recorded systems run on the thread-per-trajectory kernels: n_state <= 16, n_par <= 256");
+        family = FAM_TAPE;
+        break;
     default:
         return fail(VA_E_UNSUPPORTED, "system kind not available in this build");
     }
@@ -404,6 +432,13 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         e->threads = 128;
         e->desc.ckpt_policy = VA_CKPT_RECOMPUTE;
     }
+    if (family == FAM_TAPE) {
+        cudaFree(0); // make the primary context current for the driver API
+        std::string log;
+        const int rc = va_jit_compile(desc->tape_cuda_src, tab.s, tab.fsal, tab.s_adj, &e->jit, log);
+        if (rc != 0) return bail(VA_E_NVRTC, "tape -> CUDA compilation failed: " + log);
+        e->desc.tape_cuda_src = nullptr; // not kept
+    }
     *out = e;
     return VA_OK;
 }
@@ -425,6 +460,7 @@ void va_engine_destroy(va_engine *e)
     }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+    va_jit_destroy(e->jit);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -479,7 +515,7 @@ int va_forward_batch(va_engine *e, const va_batch_args *a)
     const cudaMemcpyKind out_kind = a->mem == VA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     VA_CUDA(cudaMemcpyAsync(e->se_x0.p, a->x0, (size_t)B * n * 8, in_kind, e->s_comp));
     VA_CUDA(cudaMemcpyAsync(e->se_par.p, a->params, (size_t)B * npar * 8, in_kind, e->s_comp));
-    if (e->family == FAM_SCALAR) {
+    if (e->family != FAM_GLV_WIDE) {
         if (int rc = ensure_workspace(e, B)) return rc;
         if (e->arena_traj < B) return fail(VA_E_NOMEM, "checkpoint arena too small for a split forward/adjoint of this batch; use va_forward_adjoint_batch");
     }
@@ -526,7 +562,7 @@ int va_adjoint_batch(va_engine *e, const va_batch_args *a)
     if (a->objective == VA_OBJ_SEED)
         VA_CUDA(cudaMemcpyAsync(e->se_lam.p, a->lambda, (size_t)B * nout * n * 8, in_kind, e->s_comp));
     VA_CUDA(cudaEventRecord(e->ev_t0, e->s_comp));
-    if (e->family == FAM_SCALAR) {
+    if (e->family != FAM_GLV_WIDE) {
         // reverse kernel over the checkpoints of the session
         VaScalarArgs s;
         std::memset(&s, 0, sizeof(s));
@@ -541,7 +577,7 @@ int va_adjoint_batch(va_engine *e, const va_batch_args *a)
         } else {
             s.mu = e->se_mu.as<double>();
         }
-        VA_CUDA(va_scalar_adjoint(s, e->s_comp));
+        if (int rc = scalar_adjoint(e, s, e->s_comp)) return rc;
         ++e->launches;
         if (sum) {
             VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), B, (int64_t)nout * npar, (int64_t)nout * npar, e->se_mu.as<double>(), 0, e->s_comp));
@@ -577,7 +613,7 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     if (!t && !x) return VA_OK;
     if (capacity < T + 1) return fail(VA_E_INVALID, "capacity too small");
     VA_CUDA(cudaSetDevice(e->device));
-    if (e->family == FAM_SCALAR) {
+    if (e->family != FAM_GLV_WIDE) {
         const size_t pitch = (size_t)e->arena_traj * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, e->ck_t.as<double>() + b, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) VA_CUDA(cudaMemcpy2D(x, 8, e->ck_x.as<double>() + b, pitch, 8, (size_t)(T + 1) * n, cudaMemcpyDeviceToHost));
@@ -592,6 +628,18 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
             std::memcpy(x + (size_t)T * n, e->se_xf_host.data() + (size_t)b * n, (size_t)n * 8);
         }
     }
+    return VA_OK;
+}
+
+int va_tape_compile_check(const char *tape_cuda_src, int32_t stepper, char *log, int32_t log_capacity)
+{
+    if (!tape_cuda_src) return fail(VA_E_INVALID, "null source");
+    VaTableau tab;
+    if (va_tableau_host(stepper, &tab) != 0) return fail(VA_E_UNSUPPORTED, "This stepper is not supported yet!");
+    std::string l;
+    const int rc = va_jit_compile(tape_cuda_src, tab.s, tab.fsal, tab.s_adj, nullptr, l);
+    if (log && log_capacity > 0) std::snprintf(log, (size_t)log_capacity, "%s", l.c_str());
+    if (rc != 0) return fail(VA_E_NVRTC, "tape -> CUDA compilation failed: " + l);
     return VA_OK;
 }
 

@@ -12,8 +12,10 @@
 // VA_POW_FMA selects the variant glibc picks at run time on an FMA-capable x86-64 (ifunc __pow_fma); without it the
 // Dekker-split variant of the generic build is used.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <math.h>
 #include <stdint.h>
+#endif
 
 #include "va_pow_tables.h"
 
@@ -38,8 +40,10 @@ typedef struct { double invc, logc, logctail; } va_pow_logtab;
 __device__ const va_pow_logtab va_pow_log_tab_d[128] = VA_POW_LOG_TAB;
 __device__ const uint64_t va_pow_exp_tab_d[256] = VA_EXP_TAB;
 #endif
+#ifndef __CUDACC_RTC__
 static const va_pow_logtab va_pow_log_tab_h[128] = VA_POW_LOG_TAB;
 static const uint64_t va_pow_exp_tab_h[256] = VA_EXP_TAB;
+#endif
 
 VA_POW_HD uint64_t va_asuint64(double f)
 {

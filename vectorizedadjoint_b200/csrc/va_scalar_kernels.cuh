@@ -1,0 +1,265 @@
+// va_scalar_kernels.cuh -- thread-per-trajectory forward / reverse sweeps, generic in the system functor.
+//
+// Included by va_scalar.cu (ahead-of-time instantiations for the built-in systems) AND handed to NVRTC together with a
+// generated functor (va_tape.hpp -> Tape::cuda_source) for recorded systems (va_jit.cpp). Keep it free of host-only code.
+//
+// One GPU lane integrates one parameter set ("one trajectory per lane", mirroring the reference's SIMD lanes but on
+// the parameter-set axis). State, stage slopes and stage adjoints live in registers; checkpoints go to a global arena
+// with the trajectory index fastest, so every lane-parallel access is coalesced.
+//
+// Forward: reference lib/include/detail/runge_kutta.hpp:38-72 (fixed step) and :76-118 (adaptive) with odeint's
+//          controlled_runge_kutta::try_step, default_error_checker, default_step_adjuster and failed_step_checker
+//          restated per lane. Arithmetic order of the stage / solution / error sums is odeint's
+//          ((1*x + (a_m0 dt) k_0) + (a_m1 dt) k_1) + ...; compiled with -fmad=false so that no FMA contraction changes
+//          an accept/reject decision; pow() is glibc's bit for bit (va_pow.h).
+// Reverse: reference lib/include/detail/backpropagation.hpp:24-64 (stage recompute from the stored x_n),
+//          :160-229 (one-step adjoint), :256-278 (loop over accepted steps), :280-348 (seeds -> lambda, mu).
+//          The AADC vector-Jacobian product (lib/include/AadData.hpp:332-373) is the functor's vjp().
+#pragma once
+#include "va_types.h"
+#include "va_pow.h"
+
+// One explicit RK step in odeint's arithmetic order. K[0] = f(x,t) on entry.
+template <class Sys, int S, bool FSAL, bool WITH_ERR>
+__device__ __forceinline__ void rk_step(const VaTableau &tab, const double *x, const double *p, double t, double dt,
+                                        double (&K)[S][Sys::N], double *xnew, double *xerr)
+{
+    constexpr int N = Sys::N;
+    constexpr int SE = FSAL ? S - 1 : S;
+    double xt[N];
+#pragma unroll
+    for (int m = 1; m < SE; ++m) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double acc = x[i];
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                const double a = tab.a[m * VA_MAX_STAGES + j];
+                if (a != 0.0) acc = acc + (a * dt) * K[j][i]; // a zero weight contributes an exact zero in odeint's sum
+            }
+            xt[i] = acc;
+        }
+        Sys::rhs(xt, p, t + dt * tab.c[m], K[m]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = x[i];
+#pragma unroll
+        for (int j = 0; j < SE; ++j) {
+            const double b = tab.b[j];
+            if (b != 0.0) acc = acc + (b * dt) * K[j][i];
+        }
+        xnew[i] = acc;
+    }
+    if (FSAL) Sys::rhs(xnew, p, t + dt, K[S - 1]);
+    if (WITH_ERR) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const double d = tab.db[j];
+                if (d != 0.0) {
+                    const double term = (dt * d) * K[j][i];
+                    acc = first ? term : acc + term;
+                    first = false;
+                }
+            }
+            xerr[i] = acc;
+        }
+    }
+}
+
+template <class Sys, int S, bool FSAL, bool ADAPTIVE>
+__device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
+{
+    constexpr int N = Sys::N, NPAR = Sys::NPAR;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const VaTableau &tab = a.tab;
+    double x[N], p[NPAR], K[S][N], xnew[N], xerr[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = a.x0[b * N + i];
+#pragma unroll
+    for (int k = 0; k < NPAR; ++k) p[k] = a.params[b * NPAR + k];
+
+    const int64_t bs = a.arena_stride;
+    double t = a.ti, dt = a.dt0;
+    const double tf = a.tf;
+    int nck = 0, count = 0, rejects = 0, status = 0;
+
+    auto push = [&]() -> bool {
+        if (nck > a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; return false; }
+        a.ck_t[(int64_t)nck * bs + b] = t;
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.ck_x[((int64_t)nck * N + i) * bs + b] = x[i];
+        ++nck;
+        return true;
+    };
+
+    if (!ADAPTIVE) {
+        // detail/runge_kutta.hpp:51-71: t = ti + step*dt (no accumulation of dt)
+        while (va_less_eq_with_sign(t + dt, tf, dt)) {
+            if (!push()) break;
+            Sys::rhs(x, p, t, K[0]);
+            rk_step<Sys, S, FSAL, false>(tab, x, p, t, dt, K, xnew, xerr);
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = xnew[i];
+            ++count;
+            t = a.ti + (double)count * dt;
+        }
+        if (!status) push();
+    } else {
+        // detail/runge_kutta.hpp:92-117, one attempt (try_step) per loop trip so that lanes stay converged
+        bool active = va_less_with_sign(t, tf, dt);
+        bool fresh = true, first_call = true;
+        int trials = 0;
+        while (active) {
+            if (fresh) {
+                if (!push()) break;
+                if (va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
+                trials = 0;
+                fresh = false;
+            }
+            if (!FSAL || first_call) { Sys::rhs(x, p, t, K[0]); first_call = false; }
+            rk_step<Sys, S, FSAL, true>(tab, x, p, t, dt, K, xnew, xerr);
+            // default_error_checker::error (a_x = a_dxdt = 1), max norm
+            double err = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double e = fabs(xerr[i]) / (a.eps_abs + a.eps_rel * (fabs(x[i]) + fabs(dt) * fabs(K[0][i])));
+                err = fmax(err, e);
+            }
+            if (err > 1.0) {
+                // default_step_adjuster::decrease_step
+                dt *= fmax(0.9 * va_pow(err, -1.0 / ((double)tab.error_order - 1.0)), 0.2);
+                ++rejects;
+                if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; } // failed_step_checker
+            } else {
+                t += dt;
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] = xnew[i];
+                if (FSAL) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) K[0][i] = K[S - 1][i];
+                }
+                // default_step_adjuster::increase_step
+                if (err < 0.5) {
+                    err = fmax(va_pow(5.0, -(double)tab.stepper_order), err);
+                    dt *= 9.0 / 10.0 * va_pow(err, -1.0 / (double)tab.stepper_order);
+                }
+                ++count;
+                fresh = true;
+                active = va_less_with_sign(t, tf, dt);
+            }
+        }
+        if (!status) push();
+    }
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) finite = finite && isfinite(x[i]);
+    if (!finite) status |= VA_TRAJ_NONFINITE;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.x_final[b * N + i] = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS) ? nan("") : x[i];
+    a.n_accept[b] = count;
+    a.n_reject[b] = rejects;
+    a.status[b] = status;
+}
+
+// One thread per (trajectory, cost function).
+template <class Sys, int S>
+__device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
+{
+    constexpr int N = Sys::N, NPAR = Sys::NPAR;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = a.B * a.n_out;
+    if (w >= total) return;
+    // cost function index slowest: neighbouring lanes read neighbouring trajectories' checkpoints
+    const int o = (int)(w / a.B);
+    const int64_t b = w - (int64_t)o * a.B;
+    const VaTableau &tab = a.tab;
+    const int64_t bs = a.arena_stride;
+    double *lam_io = a.lambda + (b * a.n_out + o) * N;
+    double *mu_out = a.mu + (b * a.n_out + o) * NPAR;
+
+    double p[NPAR], lam[N], mu[NPAR];
+#pragma unroll
+    for (int k = 0; k < NPAR; ++k) { p[k] = a.params[b * NPAR + k]; mu[k] = 0.0; }
+    if (a.status[b] & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) lam_io[i] = nan("");
+#pragma unroll
+        for (int k = 0; k < NPAR; ++k) mu_out[k] = nan("");
+        return;
+    }
+    const int T = a.n_accept[b];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (a.objective == VA_OBJ_SUM) lam[i] = 1.0;
+        else if (a.objective == VA_OBJ_HALF_NORM2) lam[i] = a.x_final[b * N + i];
+        else lam[i] = lam_io[i];
+    }
+    double K[S][N], W[S + 1][N], u[N], xm[N], gx[N];
+    double t_next = a.ck_t[(int64_t)T * bs + b];
+    for (int n = T - 1; n >= 0; --n) {
+        const double time = a.ck_t[(int64_t)n * bs + b];
+        const double dt = t_next - time; // StateStorage::GetDt: difference of stored times
+        t_next = time;
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[i] = a.ck_x[((int64_t)n * N + i) * bs + b];
+        // stage recompute, detail/backpropagation.hpp:37-52. The reference passes t_n to every stage (:48) and indexes
+        // c(m) off by one in the VJP (:127); harmless there because its examples are autonomous. Here stage m is
+        // evaluated at t_n + c_m dt, so recorded non-autonomous systems differentiate correctly.
+#pragma unroll
+        for (int m = 0; m < S; ++m) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) xm[i] = u[i];
+#pragma unroll
+            for (int j = 0; j < m; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[m * VA_MAX_STAGES + j] * K[j][i];
+            Sys::rhs(xm, p, time + tab.c[m] * dt, K[m]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            W[0][i] = lam[i];
+#pragma unroll
+            for (int m = 1; m <= S; ++m) W[m][i] = tab.b[m - 1] * dt * lam[i];
+        }
+#pragma unroll
+        for (int m = S; m > 0; --m) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) xm[i] = u[i];
+#pragma unroll
+            for (int k = 1; k < m; ++k)
+#pragma unroll
+                for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * K[k - 1][i];
+            Sys::vjp(xm, p, time + tab.c[m - 1] * dt, W[m], gx, mu);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                W[0][i] += gx[i];
+#pragma unroll
+                for (int k = 1; k < m; ++k) W[k][i] += gx[i] * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * dt;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) lam[i] = W[0][i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) lam_io[i] = lam[i];
+#pragma unroll
+    for (int k = 0; k < NPAR; ++k) mu_out[k] = mu[k];
+}
+
+
+template <class Sys, int S, bool FSAL, bool ADAPTIVE>
+__global__ void __launch_bounds__(128) k_scalar_forward(const __grid_constant__ VaScalarArgs a)
+{
+    scalar_forward_body<Sys, S, FSAL, ADAPTIVE>(a);
+}
+template <class Sys, int S>
+__global__ void __launch_bounds__(128) k_scalar_adjoint(const __grid_constant__ VaScalarArgs a)
+{
+    scalar_adjoint_body<Sys, S>(a);
+}

@@ -66,6 +66,7 @@ class Driver
     int fwd_system = -1, fwd_stepper = -1, fwd_adaptive = 0;
     double fwd_eps_abs = 0, fwd_eps_rel = 0, fwd_ti = 0, fwd_tf = 0, fwd_dt0 = 0;
     std::vector<double> fwd_x0;
+    std::string fwd_tape_src; // CUDA source of the recorded functor (tape path)
     int device = 0;
     int max_steps = 0; // 0: engine default
 

@@ -46,6 +46,7 @@ std::vector<std::vector<double>> computeSensitivityMatrix(Driver &driver, const 
     va_engine_desc d{};
     d.system = driver.fwd_system; d.n_state = Nin; d.n_par = Npar; d.n_out = Nin; d.stepper = driver.fwd_stepper; d.adaptive = driver.fwd_adaptive;
     d.eps_abs = driver.fwd_eps_abs; d.eps_rel = driver.fwd_eps_rel; d.device = driver.device; d.max_steps = driver.max_steps;
+    d.tape_cuda_src = driver.fwd_system == va::SYS_TAPE ? driver.fwd_tape_src.c_str() : nullptr;
     va_engine *e = nullptr;
     detail_runge_kutta::check(va_engine_create(&d, &e), "va_engine_create");
     std::unique_ptr<va_engine, EngineDeleter> guard(e);

@@ -24,23 +24,27 @@ size_t run_forward(int stepper_id, int adaptive, double eps_abs, double eps_rel,
     const int n = driver.GetNin(), npar = driver.GetNpar();
     // which device functor: record the functor once (cheap, B = 1) unless the caller already did
     int kind;
+    std::string tape_src;
     if (driver.p_aad_data) {
         kind = driver.p_aad_data->system_kind;
+        if (kind == va::SYS_TAPE) tape_src = driver.p_aad_data->tape.cuda_source("VaUserSys");
     } else {
-        kind = va::identify(va::record(system, n, npar));
+        const va::Tape tape = va::record(system, n, npar);
+        kind = va::identify(tape);
+        if (kind == va::SYS_TAPE) tape_src = tape.cuda_source("VaUserSys");
     }
-    if (kind == va::SYS_TAPE)
-        throw std::runtime_error("this right-hand side is not one of the built-in device functors (harmonic oscillator, Van der Pol, "
-                                 "generalized Lotka-Volterra); the tape->CUDA path is not enabled in this build");
-    const bool reuse = driver.engine && driver.fwd_system == kind && driver.fwd_stepper == stepper_id && driver.fwd_adaptive == adaptive &&
+    // a recorded system gets its own run-time compiled kernels (tape -> CUDA -> NVRTC), never reused across functors
+    const bool reuse = kind != va::SYS_TAPE && driver.engine && driver.fwd_system == kind && driver.fwd_stepper == stepper_id && driver.fwd_adaptive == adaptive &&
                        driver.fwd_eps_abs == eps_abs && driver.fwd_eps_rel == eps_rel;
     if (!reuse) {
         va_engine_desc d{};
         d.system = kind; d.n_state = n; d.n_par = npar; d.n_out = driver.GetNout(); d.stepper = stepper_id; d.adaptive = adaptive;
         d.eps_abs = eps_abs; d.eps_rel = eps_rel; d.device = driver.device; d.max_steps = driver.max_steps;
+        d.tape_cuda_src = kind == va::SYS_TAPE ? tape_src.c_str() : nullptr;
         va_engine *e = nullptr;
         check(va_engine_create(&d, &e), "va_engine_create");
         driver.engine.reset(e);
+        driver.fwd_tape_src = tape_src;
         driver.fwd_system = kind; driver.fwd_stepper = stepper_id; driver.fwd_adaptive = adaptive;
         driver.fwd_eps_abs = eps_abs; driver.fwd_eps_rel = eps_rel;
     }
