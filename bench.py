@@ -33,6 +33,20 @@ TI, TF, DT0 = 0.0, 10.0, 1e-3
 SEED = 1234
 STAGES = 6
 
+# Other BASELINE.json configs, measured with the same harness (`--workload`); the default (glv64) is the contract line.
+#   name: (system, n_state, stepper, adaptive, tol, ti, tf, dt0, max_steps, objective, stages, description)
+WORKLOADS = {
+    "glv64": (2, 64, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6, None),
+    "glv16": (2, 16, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
+              "GLV N=16 (Npar=272), 2^20 parameter sets, cash_karp54 controlled rtol=atol=1e-8, t=[0,10], full r and A gradient"),
+    "glv256": (2, 256, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
+               "GLV N=256 (Npar=65792), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; streamed-matrix kernel family; default batch 8192"),
+    "vdp": (1, 2, 3, True, 1e-8, 0.0, 0.5, 1e-3, 1024, 1, 7,
+            "Van der Pol, mu swept over [1,1024), 2^20 parameter sets, dopri5 controlled rtol=atol=1e-8, t=[0,0.5], dt0=1e-3"),
+    "harmonic": (0, 2, 1, False, 0.0, 0.0, 10.0, 0.01, 1024, 2, 4,
+                 "damped harmonic oscillator, 2^20 parameter sets, fixed-step RK4 dt=0.01, t=[0,10] (1000 steps), J=|r(tf)|^2/2"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -42,6 +56,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="total parameter sets (all ranks)")
     ap.add_argument("--reduce", default="sum", choices=["sum", "none"])
+    ap.add_argument("--workload", default="glv64", choices=sorted(WORKLOADS), help="glv64 = the headline contract line")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="parameter sets per reference-arm step (0 = auto)")
@@ -196,10 +211,78 @@ class ClockSampler:
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------------------
 
+def side_workload(args):
+    """The other BASELINE configs (single GPU, device-resident): same timing rules, one JSON line, not the contract line."""
+    import torch
+    import vectorizedadjoint_b200 as va
+    system, n, stepper, adaptive, tol, ti, tf, dt0, max_steps, objective, stages, desc = WORKLOADS[args.workload]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B = args.batch if (args.workload != "glv256" or args.batch != 1 << 20) else 8192
+    npar = va.npar_of(system, n)
+    red = va.REDUCE_SUM if args.reduce == "sum" else va.REDUCE_NONE
+    f64 = dict(dtype=torch.float64, device=dev)
+    params, x0 = torch.empty(B, npar, **f64), torch.empty(B, n, **f64)
+    va.synth_batch_device(system, n, SEED, 0, B, params, x0)
+    x_final, lam = torch.empty(B, n, **f64), torch.empty(B, 1, n, **f64)
+    mu = torch.empty((1, npar) if red == va.REDUCE_SUM else (B, 1, npar), **f64)
+    n_acc, n_rej, status = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3))
+    eng = va.Engine(system, n, stepper, adaptive, tol, tol, device=0, max_steps=max_steps)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+
+    def step():
+        eng.call("va_forward_adjoint_batch", B, x0, params, ti, tf, dt0, x_final, lam, mu, objective, red, n_acc, n_rej, status,
+                 stream=side.cuda_stream)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.info()["kernel_launches"]
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop()
+    T, R = int(n_acc.sum(dtype=torch.int64)), int(n_rej.sum(dtype=torch.int64))
+    info = eng.info()
+    line = {"metric": f"fwd+adjoint gradients/sec, {args.workload} batch {B}", "value": B / (ms * 1e-3), "unit": "gradients/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "batch_total": B, "reduce": args.reduce}, "gpu_launches": info["kernel_launches"] - l0,
+            "mean_accepted_steps": T / B, "mean_rejected": R / B, "max_accepted_steps": int(n_acc.max()),
+            "failed_trajectories": int((status != 0).sum()), "clocks": clk}
+    if system == va.SYS_GLV:
+        f_rhs, f_vjp = 2 * n * n + 2 * n, 4 * n * n + 3 * n
+        flops = (stages * T + (stages - 1) * R) * f_rhs + stages * T * f_vjp
+        peak = va.measure_fp64_peak(0)
+        line["roofline"] = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                            "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None}
+    else:
+        # thread-per-trajectory family: compulsory HBM bytes are the checkpoints, written by the forward kernel and read back
+        # by the reverse kernel: 2 * 8 * (N+1) * (T + B) bytes (+ inputs/outputs)
+        byts = 2 * 8 * (n + 1) * (T + B) + B * 8 * (npar + 3 * n + npar)
+        hbm = None
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        ach = byts / (ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if hbm else None, "traffic": None,
+                            "note": "checkpoint arena traffic 2*8*(N+1) B per accepted step and trajectory"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.workload != "glv64":
+        side_workload(args)
         return
     import torch
     import torch.distributed as dist

@@ -333,3 +333,44 @@ def test_glv_full_size_properties(va):
     assert_close(xf[idx].cpu().numpy(), o["x_final"], what="x(tf)")
     assert_close(mu1[idx, 0].cpu().numpy(), o["mu"], what="mu")
     assert_close(lam1[idx, 0].cpu().numpy(), o["lam"], what="lambda")
+
+
+@pytest.mark.parametrize("N,B,stepper,adaptive,tol,tf,dt0", [(100, 6, 2, True, 1e-8, 10.0, 1e-3), (256, 3, 2, True, 1e-8, 10.0, 1e-3),
+                                                            (256, 2, 3, True, 1e-6, 10.0, 1e-3), (80, 4, 1, False, 0.0, 0.3, 0.01)])
+def test_glv_large_species_counts_streamed_matrix(va, N, B, stepper, adaptive, tol, tf, dt0):
+    """N > 64 (BASELINE config 5 uses N = 256): the matrix no longer fits one SM's registers and is streamed from L2/HBM."""
+    p = oracle.synth_params(oracle.SYS_GLV, N, 2024, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_SUM, threads=8)
+    with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol) as e:
+        assert e.info()["kernel_family"] == 2
+        r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
+        s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+    assert (r["status"] == 0).all()
+    np.testing.assert_array_equal(r["n_accept"], o["n_accept"])
+    assert_close(r["x_final"], o["x_final"], what="x(tf)")
+    assert_close(r["lam"][:, 0], o["lam"], what="lambda")
+    assert_close(r["mu"][:, 0], o["mu"], what="mu")
+    assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
+
+
+def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
+    """The two GLV kernel families are independent implementations: cross-check them at N = 64."""
+    N, B = 64, 40
+    p = oracle.synth_params(oracle.SYS_GLV, N, 5150, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        assert e.info()["kernel_family"] == 1
+        w = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2)
+    monkeypatch.setenv("VA_GLV_FORCE_STREAM", "1")
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        assert e.info()["kernel_family"] == 2
+        s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2)
+        f = e.forward(x0, p, 0.0, 10.0, 1e-3)
+        t, x = e.checkpoints(3)
+    np.testing.assert_array_equal(w["n_accept"], s["n_accept"])
+    assert_close(w["x_final"], s["x_final"], rtol=1e-12, what="x(tf)")
+    assert_close(w["lam"][:, 0], s["lam"][:, 0], rtol=1e-11, what="lambda")
+    assert_close(w["mu"][:, 0], s["mu"][:, 0], rtol=1e-11, what="mu")
+    assert len(t) == f["n_accept"][3] + 1 and t[0] == 0.0
+    np.testing.assert_array_equal(x[0], x0[3])

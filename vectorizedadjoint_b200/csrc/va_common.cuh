@@ -20,17 +20,23 @@ struct VaGlvWideArgs {
     const double *x0, *params;
     double *x_final, *lambda, *mu;
     int32_t *n_accept, *n_reject, *status;
-    double *slab;         // grid * slab_stride doubles
+    double *slab;         // (grid * slots per CTA) * slab_stride doubles
     int64_t slab_stride;
-    double *partial;      // VA_REDUCE_SUM: [grid][n_par] per-CTA partial sums (reduced by va_reduce_rows)
+    double *partial;      // VA_REDUCE_SUM: [grid * slots per CTA][n_par] per-CTA partial sums (reduced by va_reduce_rows)
     int grid;
     struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);
-int va_glv_wide_block_doubles(int stepper); // step block: [8-double header (t_n) | X_0..X_{s-1} | g_0..g_{s-1}], 64 wide
-cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads);
+int va_glv_wide_padded(int n);                      // padded species count the kernel runs with (16, 32 or 64)
+int va_glv_wide_block_doubles(int n, int stepper); // step block: [8-double header (t_n) | X_0..X_{s-1} | g_0..g_{s-1}], padded width
+cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);
 cudaError_t va_glv_wide_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
+// streamed-matrix GLV family (va_glv_stream.cu): any N, one 256-thread CTA per trajectory, same argument block
+bool va_glv_stream_supported(int n, int stepper, int adaptive);
+int va_glv_stream_block_doubles(int n, int stepper);
+cudaError_t va_glv_stream_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
 // out[k] (+)= sum_{g<G} in[g*stride + k], deterministic order
 cudaError_t va_reduce_rows(const double *in, int64_t G, int64_t stride, int64_t n, double *out, int accumulate, cudaStream_t st);

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -39,7 +40,7 @@ int fail(int code, const std::string &msg)
                         std::string(#call) + ": " + cudaGetErrorString(err__));                             \
     } while (0)
 
-enum Family { FAM_SCALAR = 0, FAM_GLV_WIDE = 1, FAM_TAPE = 3 }; // TAPE: scalar kernels compiled at run time for a recorded system
+enum Family { FAM_SCALAR = 0, FAM_GLV_WIDE = 1, FAM_GLV_STREAM = 2, FAM_TAPE = 3 }; // TAPE: scalar kernels compiled at run time for a recorded system
 
 struct DevBuf {
     void *p = nullptr;
@@ -77,7 +78,7 @@ struct va_engine {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // wide family
-    int grid = 0, ctas_per_sm = 0, threads = 0;
+    int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1; // tpc: trajectories (slots) per CTA
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -100,14 +101,16 @@ struct va_engine {
 
 namespace {
 
+bool is_glv(const va_engine *e) { return e->family == FAM_GLV_WIDE || e->family == FAM_GLV_STREAM; }
+
 int64_t per_traj_arena_bytes(const va_engine *e) { return (int64_t)(e->cap + 1) * (e->desc.n_state + 1) * 8; }
 
 int ensure_workspace(va_engine *e, int64_t B)
 {
-    if (e->family == FAM_GLV_WIDE) {
-        const size_t need = (size_t)e->grid * e->slab_stride * 8;
+    if (is_glv(e)) {
+        const size_t need = (size_t)e->grid * e->tpc * e->slab_stride * 8;
         if (int rc = e->slab.ensure(need)) return rc;
-        if (int rc = e->partial.ensure((size_t)e->grid * e->desc.n_par * 8)) return rc;
+        if (int rc = e->partial.ensure((size_t)e->grid * e->tpc * e->desc.n_par * 8)) return rc;
         e->workspace_bytes = (int64_t)(e->slab.bytes + e->partial.bytes);
         e->chunk_traj = B;
         return VA_OK;
@@ -173,14 +176,14 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
     if (d.B <= 0) return VA_OK;
     if (int rc = ensure_workspace(e, d.B)) return rc;
     int32_t *acc = d.n_accept, *rej = d.n_reject, *sta = d.status;
-    if (e->family != FAM_GLV_WIDE) { // the reverse kernel needs them
+    if (!is_glv(e)) { // the reverse kernel needs them
         if (!acc) { if (int rc = e->own_accept.ensure((size_t)d.B * 4)) return rc; acc = e->own_accept.as<int32_t>(); }
         if (!rej) { if (int rc = e->own_reject.ensure((size_t)d.B * 4)) return rc; rej = e->own_reject.as<int32_t>(); }
         if (!sta) { if (int rc = e->own_status.ensure((size_t)d.B * 4)) return rc; sta = e->own_status.as<int32_t>(); }
     }
     const bool sum = d.reduce == VA_REDUCE_SUM;
 
-    if (e->family == FAM_GLV_WIDE) {
+    if (is_glv(e)) {
         VaGlvWideArgs a;
         std::memset(&a, 0, sizeof(a));
         a.n = n; a.stepper = e->desc.stepper; a.adaptive = e->desc.adaptive; a.n_out = d.forward_only ? 0 : nout;
@@ -189,7 +192,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.B = d.B; a.cap = e->cap; a.x0 = d.x0; a.params = d.params; a.x_final = d.x_final; a.lambda = d.lambda;
         a.n_accept = acc; a.n_reject = rej; a.status = sta;
         a.slab = e->slab.as<double>(); a.slab_stride = e->slab_stride; a.partial = e->partial.as<double>();
-        a.grid = (int)std::min<int64_t>(e->grid, d.B);
+        a.grid = (int)std::min<int64_t>(e->grid, (d.B + e->tpc - 1) / e->tpc);
         const bool native_sum = sum && nout == 1 && !d.forward_only;
         if (sum && !native_sum && !d.forward_only) {
             // several cost functions per trajectory: per-trajectory gradients into a scratch buffer, then a row reduction
@@ -200,10 +203,11 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
             a.reduce = native_sum ? VA_REDUCE_SUM : VA_REDUCE_NONE;
             a.mu = d.mu;
         }
-        VA_CUDA(va_glv_wide_forward_adjoint(a, st));
+        if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
+        else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
         ++e->launches;
         if (native_sum) {
-            VA_CUDA(va_reduce_rows(e->partial.as<double>(), a.grid, npar, npar, d.mu, d.mu_accumulate ? 1 : 0, st));
+            VA_CUDA(va_reduce_rows(e->partial.as<double>(), (int64_t)a.grid * e->tpc, npar, npar, d.mu, d.mu_accumulate ? 1 : 0, st));
             ++e->launches;
         } else if (sum && !d.forward_only) {
             VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), d.B, (int64_t)nout * npar, (int64_t)nout * npar, d.mu,
@@ -269,7 +273,7 @@ int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
     const int64_t out_bytes = 8LL * n + 8LL * nout * n + (sum ? 0 : 8LL * nout * npar) + 12;
     const int64_t slot_budget = 2LL << 30;
     int64_t Bc = std::max<int64_t>(1, slot_budget / (in_bytes + out_bytes));
-    if (e->family == FAM_GLV_WIDE && Bc > e->grid) Bc = Bc / e->grid * e->grid; // whole waves of CTAs
+    if (is_glv(e) && Bc > (int64_t)e->grid * e->tpc) Bc = Bc / (e->grid * e->tpc) * (e->grid * e->tpc); // whole waves
     Bc = std::min(Bc, B);
     if (B == 0) return VA_OK;
     for (int s = 0; s < 2; ++s) {
@@ -385,9 +389,12 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         break;
     case VA_SYS_GLV:
         if (desc->n_par != desc->n_state * desc->n_state + desc->n_state) return fail(VA_E_INVALID, "GLV: n_par must be N*N + N");
-        if (!va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive))
-            return fail(VA_E_UNSUPPORTED, "GLV: supported are N <= 64 with rk4 (fixed step), cash_karp54 or dopri5 (controlled)");
-        family = FAM_GLV_WIDE;
+        if (va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_FORCE_STREAM"))
+            family = FAM_GLV_WIDE; // N <= 64: matrix in registers
+        else if (va_glv_stream_supported(desc->n_state, desc->stepper, desc->adaptive))
+            family = FAM_GLV_STREAM; // any N: matrix streamed from L2/HBM
+        else
+            return fail(VA_E_UNSUPPORTED, "GLV: supported steppers are rk4 (fixed step), cash_karp54 and dopri5 (controlled)");
         break;
     case VA_SYS_TAPE:
         if (!desc->tape_cuda_src) return fail(VA_E_INVALID, "VA_SYS_TAPE needs tape_cuda_src (va::Tape::cuda_source(\"VaUserSys\"))");
@@ -410,7 +417,7 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
     e->tab = tab;
     e->family = family;
     e->device = desc->device;
-    e->cap = desc->max_steps > 0 ? desc->max_steps : (family == FAM_GLV_WIDE ? 256 : 2048);
+    e->cap = desc->max_steps > 0 ? desc->max_steps : (family == FAM_GLV_WIDE || family == FAM_GLV_STREAM ? 256 : 2048);
     auto bail = [&](int code, const std::string &m) { va_engine_destroy(e); return fail(code, m); };
     if (cudaSetDevice(e->device) != cudaSuccess) return bail(VA_E_CUDA, "cudaSetDevice failed");
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device);
@@ -423,8 +430,15 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
              cudaEventCreateWithFlags(&e->ev_comp[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&e->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) return bail(VA_E_CUDA, "stream/event creation failed");
-    if (family == FAM_GLV_WIDE) {
-        cudaError_t ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads);
+    if (family == FAM_GLV_STREAM) {
+        e->ctas_per_sm = 2;
+        e->grid = e->sm_count * e->ctas_per_sm;
+        e->threads = 256;
+        e->tpc = 1;
+        e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper);
+        e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
+    } else if (family == FAM_GLV_WIDE) {
+        cudaError_t ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
         if (ce != cudaSuccess) return bail(VA_E_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(ce));
         e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
         e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
@@ -502,7 +516,7 @@ int va_forward_batch(va_engine *e, const va_batch_args *a)
     VA_CUDA(cudaSetDevice(e->device));
     const int n = e->desc.n_state, npar = e->desc.n_par;
     const int64_t B = a->batch;
-    if (e->family == FAM_GLV_WIDE && B > e->grid)
+    if (is_glv(e) && B > (int64_t)e->grid * e->tpc)
         return fail(VA_E_UNSUPPORTED, "split forward/adjoint on the GLV path keeps checkpoints for at most one wave of CTAs; "
                                       "use va_forward_adjoint_batch for larger batches");
     if (int rc = e->se_x0.ensure((size_t)B * n * 8)) return rc;
@@ -515,7 +529,7 @@ int va_forward_batch(va_engine *e, const va_batch_args *a)
     const cudaMemcpyKind out_kind = a->mem == VA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     VA_CUDA(cudaMemcpyAsync(e->se_x0.p, a->x0, (size_t)B * n * 8, in_kind, e->s_comp));
     VA_CUDA(cudaMemcpyAsync(e->se_par.p, a->params, (size_t)B * npar * 8, in_kind, e->s_comp));
-    if (e->family != FAM_GLV_WIDE) {
+    if (!is_glv(e)) {
         if (int rc = ensure_workspace(e, B)) return rc;
         if (e->arena_traj < B) return fail(VA_E_NOMEM, "checkpoint arena too small for a split forward/adjoint of this batch; use va_forward_adjoint_batch");
     }
@@ -562,7 +576,7 @@ int va_adjoint_batch(va_engine *e, const va_batch_args *a)
     if (a->objective == VA_OBJ_SEED)
         VA_CUDA(cudaMemcpyAsync(e->se_lam.p, a->lambda, (size_t)B * nout * n * 8, in_kind, e->s_comp));
     VA_CUDA(cudaEventRecord(e->ev_t0, e->s_comp));
-    if (e->family != FAM_GLV_WIDE) {
+    if (!is_glv(e)) {
         // reverse kernel over the checkpoints of the session
         VaScalarArgs s;
         std::memset(&s, 0, sizeof(s));
@@ -613,7 +627,7 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     if (!t && !x) return VA_OK;
     if (capacity < T + 1) return fail(VA_E_INVALID, "capacity too small");
     VA_CUDA(cudaSetDevice(e->device));
-    if (e->family != FAM_GLV_WIDE) {
+    if (!is_glv(e)) {
         const size_t pitch = (size_t)e->arena_traj * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, e->ck_t.as<double>() + b, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) VA_CUDA(cudaMemcpy2D(x, 8, e->ck_x.as<double>() + b, pitch, 8, (size_t)(T + 1) * n, cudaMemcpyDeviceToHost));
@@ -621,7 +635,8 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
         const double *base = e->slab.as<double>() + b * e->slab_stride;
-        const size_t pitch = (size_t)va_glv_wide_block_doubles(e->desc.stepper) * 8;
+        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE ? va_glv_wide_block_doubles(n, e->desc.stepper)
+                                                                : va_glv_stream_block_doubles(n, e->desc.stepper)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {
             if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + 8, pitch, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));

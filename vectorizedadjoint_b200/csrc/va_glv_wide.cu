@@ -33,7 +33,7 @@
 // flip only when the error estimate is within ~1e-8 relative of a threshold (documented in DESIGN.md).
 #include <cstdlib>
 
-#include "va_common.cuh"
+#include "va_glv_common.cuh"
 
 #ifndef VA_GLV_LG
 #define VA_GLV_LG 8
@@ -44,91 +44,11 @@
 
 namespace {
 
-constexpr int NP = 64;   // padded species count
+constexpr int NPMAX = 64; // largest padded species count of this kernel family
 constexpr int HDR = 8;   // doubles in a step-block header (hdr[0] = t_n)
 
-// ---- compile-time tableaux: zero weights vanish from the unrolled code --------------------------------------------
-struct TabRK4 {
-    static constexpr int S = 4, SADJ = 4, STEPPER_ORDER = 4, ERROR_ORDER = 0;
-    static constexpr bool FSAL = false, HAS_ERR = false;
-    __host__ __device__ static constexpr double a(int m, int j)
-    {
-        return (m == 1 && j == 0) ? 0.5 : (m == 2 && j == 1) ? 0.5 : (m == 3 && j == 2) ? 1.0 : 0.0;
-    }
-    __host__ __device__ static constexpr double b(int j) { return (j == 0 || j == 3) ? 1.0 / 6 : 1.0 / 3; }
-    __host__ __device__ static constexpr double db(int) { return 0.0; }
-};
-struct TabCK54 {
-    static constexpr int S = 6, SADJ = 6, STEPPER_ORDER = 5, ERROR_ORDER = 4;
-    static constexpr bool FSAL = false, HAS_ERR = true;
-    __host__ __device__ static constexpr double a(int m, int j)
-    {
-        constexpr double t[6][5] = {{0, 0, 0, 0, 0},
-                                    {1.0 / 5, 0, 0, 0, 0},
-                                    {3.0 / 40, 9.0 / 40, 0, 0, 0},
-                                    {3.0 / 10, -9.0 / 10, 6.0 / 5, 0, 0},
-                                    {-11.0 / 54, 5.0 / 2, -70.0 / 27, 35.0 / 27, 0},
-                                    {1631.0 / 55296, 175.0 / 512, 575.0 / 13824, 44275.0 / 110592, 253.0 / 4096}};
-        return t[m][j];
-    }
-    __host__ __device__ static constexpr double b(int j)
-    {
-        constexpr double t[6] = {37.0 / 378, 0, 250.0 / 621, 125.0 / 594, 0, 512.0 / 1771};
-        return t[j];
-    }
-    __host__ __device__ static constexpr double db(int j)
-    {
-        constexpr double t[6] = {37.0 / 378 - 2825.0 / 27648, 0, 250.0 / 621 - 18575.0 / 48384, 125.0 / 594 - 13525.0 / 55296,
-                                 0.0 - 277.0 / 14336, 512.0 / 1771 - 1.0 / 4};
-        return t[j];
-    }
-};
-struct TabDOPRI5 {
-    static constexpr int S = 7, SADJ = 6, STEPPER_ORDER = 5, ERROR_ORDER = 4;
-    static constexpr bool FSAL = true, HAS_ERR = true;
-    __host__ __device__ static constexpr double a(int m, int j)
-    {
-        constexpr double t[7][6] = {{0, 0, 0, 0, 0, 0},
-                                    {1.0 / 5, 0, 0, 0, 0, 0},
-                                    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
-                                    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
-                                    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
-                                    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
-                                    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
-        return t[m][j];
-    }
-    __host__ __device__ static constexpr double b(int j)
-    {
-        constexpr double t[7] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0};
-        return t[j];
-    }
-    __host__ __device__ static constexpr double db(int j)
-    {
-        constexpr double t[7] = {35.0 / 384 - 5179.0 / 57600, 0, 500.0 / 1113 - 7571.0 / 16695, 125.0 / 192 - 393.0 / 640,
-                                 -2187.0 / 6784 - (-92097.0 / 339200), 11.0 / 84 - 187.0 / 2100, -1.0 / 40};
-        return t[j];
-    }
-};
-
-template <class Tab>
+template <class Tab, int NP>
 constexpr int block_doubles() { return HDR + 2 * Tab::SADJ * NP; }
-
-// e^(-1/P) for e > 0: float seed + Newton on y^-P = e (quadratic), accurate to a few ulp; replaces pow() in
-// odeint's default_step_adjuster on this path (all 256 threads evaluate it redundantly, so it has to be short).
-template <int P>
-__device__ __forceinline__ double inv_root(double e)
-{
-    if (e > 1e30) return 0.0;
-    double y = (double)__powf((float)e, -1.0f / (float)P);
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        double yp = y;
-#pragma unroll
-        for (int k = 1; k < P; ++k) yp *= y;
-        y = fma(y * (1.0 / P), fma(-e, yp, 1.0), y);
-    }
-    return y;
-}
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -194,25 +114,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// LG = lanes per reduction group: 16 -> 256 threads, 4x4 tiles; 8 -> 128 threads, 4x8 / 8x4 tiles (fewer operand and
-// shuffle wavefronts per DFMA, twice the registers per thread).
-template <class Tab, bool ADAPTIVE, bool EXACT64, int LG>
-__global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
+// NP = padded species count (16, 32 or 64); LG = lanes per reduction group. A trajectory is integrated by NTT = (NP/4) LG
+// threads (NP = 64, LG = 8: 128 threads with 4x8 / 8x4 tiles; NP = 16, LG = 8: ONE WARP with 4x2 / 2x4 tiles), and a CTA
+// hosts TPC = 128 / NTT independent trajectories ("slots"), each with its own shared buffers, barrier and slab.
+template <class Tab, bool ADAPTIVE, bool EXACT, int LG, int NP>
+__global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
 {
-    constexpr int NT = 16 * LG;      // threads per CTA
-    constexpr int TG = NP / LG;      // tile extent along the lane (g) direction: 4 or 8
-    constexpr int NW = NT / 32;
+    constexpr int NTT = (NP / 4) * LG; // threads per trajectory
+    constexpr int NT = 128;            // threads per CTA
+    constexpr int TPC = NT / NTT;      // trajectories (slots) per CTA
+    constexpr int TG = NP / LG;        // tile extent along the lane (g) direction
+    constexpr int NW = NTT / 32;       // warps per trajectory
+    static_assert(NTT >= 32 && NT % NTT == 0 && TG >= 2 && TG % 2 == 0, "unsupported tile geometry");
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
-    constexpr int BLK = block_doubles<Tab>();
-    __shared__ __align__(16) double xs[2][NP];      // stage state (forward) / v = w o x (backward), double buffered
-    __shared__ __align__(128) double xg[2][BLK];    // step blocks [hdr | X_0..X_{s-1} | g_0..g_{s-1}] streamed back by TMA
-    __shared__ double red[NW];
-    __shared__ __align__(8) uint64_t mbar[2];
+    constexpr int BLK = block_doubles<Tab, NP>();
+    __shared__ __align__(16) double xs_all[TPC][2][NP];   // stage state (forward) / v = w o x (backward), double buffered
+    __shared__ __align__(128) double xg_all[TPC][2][BLK]; // step blocks [hdr | X_0..X_{s-1} | g_0..g_{s-1}] streamed back by TMA
+    __shared__ double red_all[TPC][NW > 0 ? NW : 1];
+    __shared__ __align__(8) uint64_t mbar_all[TPC][2];
+    __shared__ int red_i_all[TPC][NW > 0 ? NW : 1];
 
-    const int tid = threadIdx.x;
+    const int slot = threadIdx.x / NTT;
+    const int tid = threadIdx.x % NTT; // thread index inside the trajectory group
+    double(*xs)[NP] = xs_all[slot];
+    double(*xg)[BLK] = xg_all[slot];
+    double *red = red_all[slot];
+    uint64_t *mbar = mbar_all[slot];
     const int g = tid & (LG - 1);    // lane inside the reduction group (column tile forward, row tile backward)
-    const int hi = tid / LG;         // the other tile coordinate, 0..15 (row tile forward, column tile backward)
+    const int hi = tid / LG;         // the other tile coordinate, 0..NP/4-1 (row tile forward, column tile backward)
     const int R = g / (LG / 4);      // tile entry (of 4) this lane ends up with after a reduction
     const int own = 4 * hi + R;      // vector component owned by this lane (LG/4 redundant lanes per component)
     const bool writer = (g & (LG / 4 - 1)) == 0;
@@ -221,7 +151,27 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
     const int n = a.n;
     const int npar = n * n + n;
     const int cap = a.cap;
-    double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
+    const int64_t gslot = (int64_t)blockIdx.x * TPC + slot; // global slot: owns one slab and one partial-sum row
+    double *const slab = a.slab + gslot * a.slab_stride;
+
+    // barrier over the threads of ONE trajectory: a warp sync when a trajectory is a single warp, else a named barrier
+    auto traj_sync = [&]() {
+        if (NTT == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(NTT) : "memory");
+    };
+    // OR over the threads of one trajectory
+    auto traj_or = [&](int v) -> int {
+        v = __reduce_or_sync(0xffffffffu, v);
+        if (NW > 1) {
+            if (lane == 0) red_i_all[slot][warp] = v;
+            traj_sync();
+            v = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v |= red_i_all[slot][w];
+            traj_sync();
+        }
+        return v;
+    };
 
     // g-direction entries of a tile: FG(e) = 2g + (e&1) + 2 LG (e>>1): the LG lanes of a group read their operands
     // as TG/2 conflict-free LDS.128 (double2 index g + LG j)
@@ -242,7 +192,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
 #pragma unroll
         for (int c = 0; c < 4; ++c) Abar[r][c] = 0.0;
 
-    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+    for (int64_t b = gslot; b < a.B; b += (int64_t)gridDim.x * TPC) {
         const double *pb = a.params + b * npar;
 
         // ================================ forward sweep =====================================
@@ -253,7 +203,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int row = 4 * hi + r;
-                if (EXACT64) {
+                if (EXACT) {
                     const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 2 * g);
 #pragma unroll
                     for (int j = 0; j < TG / 2; ++j) {
@@ -284,7 +234,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
         auto matvec = [&](double X, int m, auto &&extra) -> double { // m is a compile-time constant after unrolling
             double *buf = xs[m & 1];
             if (writer) buf[own] = X;
-            __syncthreads();
+            traj_sync();
             const double2 *xv = reinterpret_cast<const double2 *>(buf) + g;
             double xc[TG];
 #pragma unroll
@@ -383,10 +333,14 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
                 double e = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
 #pragma unroll
                 for (int d = 16; d >= LG / 4; d >>= 1) e = fmax(e, shfl_xor_d(e, d));
-                if (lane == 0) red[warp] = e;
-                __syncthreads();
+                if (NW > 1) {
+                    if (lane == 0) red[warp] = e;
+                    traj_sync();
 #pragma unroll
-                for (int w = 0; w < NW; ++w) err = fmax(err, red[w]);
+                    for (int w = 0; w < NW; ++w) err = fmax(err, red[w]);
+                } else {
+                    err = e;
+                }
                 accept = !(err > 1.0);
             }
             if (!accept) {
@@ -428,7 +382,8 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
         if (tid == 0) sp[-HDR] = t; // header of block T carries the final time
         if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
         fence_proxy_async();               // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
-        status = __syncthreads_or(status);
+        traj_sync();
+        status = traj_or(status);
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
         if (writer && own < n) a.x_final[b * n + own] = failed ? nan("") : x;
         if (tid == 0) {
@@ -446,7 +401,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
 #pragma unroll
             for (int r = 0; r < TG; ++r) {
                 const int row = FG(r);
-                if (EXACT64) {
+                if (EXACT) {
                     const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 4 * hi);
                     const double2 v0 = __ldg(src), v1 = __ldg(src + 1);
                     Ab[r][0] = v0.x; Ab[r][1] = v0.y; Ab[r][2] = v1.x; Ab[r][3] = v1.y;
@@ -473,7 +428,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
             if (failed) {
                 if (writer && own < n) lam_io[own] = nan("");
                 if (a.reduce == VA_REDUCE_NONE)
-                    for (int k = tid; k < npar; k += NT) mu_o[k] = nan("");
+                    for (int k = tid; k < npar; k += NTT) mu_o[k] = nan("");
                 continue;
             }
             double lam;
@@ -490,7 +445,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
             }
 
             // stream the step blocks back, newest first; block `step` -> buffer (T-1-step)&1, fetched one step ahead
-            if (o > 0) __syncthreads(); // the previous seed's last reads of xg[] are done before it is refilled
+            if (o > 0) traj_sync(); // the previous seed's last reads of xg[] are done before it is refilled
             if (T > 0 && tid == 0) {
                 mbar_expect_tx(&mbar[0], BLK * 8);
                 bulk_g2s(xg[0], slab + (int64_t)(T - 1) * BLK, BLK * 8, &mbar[0]);
@@ -514,7 +469,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
                 for (int m = SADJ; m >= 1; --m) {
                     double *vb = xs[m & 1];
                     if (writer) vb[own] = v;
-                    __syncthreads();
+                    traj_sync();
                     if (m == SADJ && step > 0 && tid == 0) {
                         // every thread is past its reads of the other buffer (previous step): refill it
                         mbar_expect_tx(&mbar[bufi ^ 1], BLK * 8);
@@ -572,7 +527,7 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
 #pragma unroll
                 for (int r = 0; r < TG; ++r) {
                     const int row = FG(r);
-                    if (EXACT64) {
+                    if (EXACT) {
                         double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP + 4 * hi);
                         dst[0] = make_double2(Abar[r][0], Abar[r][1]);
                         dst[1] = make_double2(Abar[r][2], Abar[r][3]);
@@ -586,11 +541,11 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
                 }
             }
         }
-        __syncthreads(); // slab and shared buffers are reused by the next trajectory
+        traj_sync(); // slab and shared buffers are reused by the next trajectory
     }
 
     if (a.reduce == VA_REDUCE_SUM) {
-        double *part = a.partial + (int64_t)blockIdx.x * npar;
+        double *part = a.partial + gslot * npar;
         if (writer && own < n) part[own] = rbar;
 #pragma unroll
         for (int r = 0; r < TG; ++r) {
@@ -606,6 +561,16 @@ __global__ void __launch_bounds__(16 * LG, VA_GLV_MINB) k_glv_wide(const __grid_
 
 constexpr int kLG = VA_GLV_LG; // lanes per reduction group, chosen at build time (csrc/Makefile)
 
+int np_of(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : 64; }
+
+template <class Tab, bool ADAPTIVE, int NP>
+cudaError_t launch_np(const VaGlvWideArgs &a, cudaStream_t st)
+{
+    if (a.n == NP) k_glv_wide<Tab, ADAPTIVE, true, kLG, NP><<<a.grid, 128, 0, st>>>(a);
+    else k_glv_wide<Tab, ADAPTIVE, false, kLG, NP><<<a.grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <class Tab, bool ADAPTIVE>
 cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
 {
@@ -617,24 +582,36 @@ cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
         a.coef.b[m] = Tab::b(m);
         a.coef.db[m] = Tab::db(m);
     }
-    if (a.n == NP) k_glv_wide<Tab, ADAPTIVE, true, kLG><<<a.grid, 16 * kLG, 0, st>>>(a);
-    else k_glv_wide<Tab, ADAPTIVE, false, kLG><<<a.grid, 16 * kLG, 0, st>>>(a);
-    return cudaGetLastError();
+    switch (np_of(a.n)) {
+    case 16: return launch_np<Tab, ADAPTIVE, 16>(a, st);
+    case 32: return launch_np<Tab, ADAPTIVE, 32>(a, st);
+    default: return launch_np<Tab, ADAPTIVE, 64>(a, st);
+    }
+}
+
+template <class Tab, bool ADAPTIVE, int NP>
+cudaError_t occupancy_np(int n, int *ctas_per_sm)
+{
+    if (n == NP) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, true, kLG, NP>, 128, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, false, kLG, NP>, 128, 0);
 }
 
 template <class Tab, bool ADAPTIVE>
 cudaError_t occupancy(int n, int *ctas_per_sm)
 {
-    if (n == NP) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, true, kLG>, 16 * kLG, 0);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_wide<Tab, ADAPTIVE, false, kLG>, 16 * kLG, 0);
+    switch (np_of(n)) {
+    case 16: return occupancy_np<Tab, ADAPTIVE, 16>(n, ctas_per_sm);
+    case 32: return occupancy_np<Tab, ADAPTIVE, 32>(n, ctas_per_sm);
+    default: return occupancy_np<Tab, ADAPTIVE, 64>(n, ctas_per_sm);
+    }
 }
 
-int block_of(int stepper)
+int sadj_of(int stepper)
 {
     switch (stepper) {
-    case VA_RK_RK4: return block_doubles<TabRK4>();
-    case VA_RK_CK54: return block_doubles<TabCK54>();
-    case VA_RK_DOPRI5: return block_doubles<TabDOPRI5>();
+    case VA_RK_RK4: return TabRK4::SADJ;
+    case VA_RK_CK54: return TabCK54::SADJ;
+    case VA_RK_DOPRI5: return TabDOPRI5::SADJ;
     }
     return 0;
 }
@@ -643,21 +620,22 @@ int block_of(int stepper)
 
 bool va_glv_wide_supported(int n, int stepper, int adaptive)
 {
-    if (n < 1 || n > NP) return false;
+    if (n < 1 || n > NPMAX) return false;
     if (stepper == VA_RK_RK4) return !adaptive;
     if (stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5) return adaptive != 0;
     return false;
 }
 
-int va_glv_wide_block_doubles(int stepper) { return block_of(stepper); }
+int va_glv_wide_padded(int n) { return np_of(n); }
+
+int va_glv_wide_block_doubles(int n, int stepper) { return HDR + 2 * sadj_of(stepper) * np_of(n); }
 
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap)
 {
-    (void)n;
-    return (int64_t)(cap + 1) * block_of(stepper); // block T holds only the final time in its header
+    return (int64_t)(cap + 1) * va_glv_wide_block_doubles(n, stepper); // block T holds only the final time in its header
 }
 
-cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads)
+cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta)
 {
     int sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -677,7 +655,8 @@ cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *c
     }
     *ctas_per_sm = occ;
     *grid = sms * occ;
-    *threads = 16 * kLG;
+    *threads = 128;
+    *slots_per_cta = 128 / ((np_of(n) / 4) * kLG);
     return cudaSuccess;
 }
 
