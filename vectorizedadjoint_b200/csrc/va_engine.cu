@@ -82,7 +82,7 @@ struct va_engine {
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
-    DevBuf ck_t, ck_x;
+    DevBuf ck_t, ck_x, work_counter; // work_counter: 2 x u64, dynamic trajectory / work-item fetch of the persistent grids
     int64_t arena_traj = 0;
     // per-trajectory bookkeeping when the caller passes NULL
     DevBuf own_accept, own_reject, own_status, mu_tmp;
@@ -139,8 +139,13 @@ int ensure_workspace(va_engine *e, int64_t B)
 }
 
 // thread-per-trajectory kernels: ahead-of-time instantiations for the built-in systems, NVRTC module for recorded ones
-int scalar_forward(va_engine *e, const VaScalarArgs &a, cudaStream_t st)
+int scalar_forward(va_engine *e, const VaScalarArgs &a_in, cudaStream_t st)
 {
+    if (int rc = e->work_counter.ensure(16)) return rc;
+    VA_CUDA(cudaMemsetAsync(e->work_counter.p, 0, 16, st));
+    VaScalarArgs a = a_in;
+    a.work_counter = e->work_counter.as<unsigned long long>();
+    a.grid_limit = e->sm_count * 16; // 16 x 128 threads = the most an SM can hold; surplus CTAs just find the queue empty
     if (e->family == FAM_TAPE) {
         if (int cr = va_jit_launch(e->jit, 0, a, a.B, st)) return fail(VA_E_CUDA, "cuLaunchKernel(forward) failed: " + std::to_string(cr));
         return VA_OK;
@@ -148,8 +153,13 @@ int scalar_forward(va_engine *e, const VaScalarArgs &a, cudaStream_t st)
     VA_CUDA(va_scalar_forward(a, st));
     return VA_OK;
 }
-int scalar_adjoint(va_engine *e, const VaScalarArgs &a, cudaStream_t st)
+int scalar_adjoint(va_engine *e, const VaScalarArgs &a_in, cudaStream_t st)
 {
+    if (int rc = e->work_counter.ensure(16)) return rc;
+    VA_CUDA(cudaMemsetAsync(e->work_counter.as<unsigned long long>() + 1, 0, 8, st));
+    VaScalarArgs a = a_in;
+    a.work_counter = e->work_counter.as<unsigned long long>();
+    a.grid_limit = e->sm_count * 16; // 16 x 128 threads = the most an SM can hold; surplus CTAs just find the queue empty
     if (e->family == FAM_TAPE) {
         if (int cr = va_jit_launch(e->jit, 1, a, a.B * a.n_out, st)) return fail(VA_E_CUDA, "cuLaunchKernel(adjoint) failed: " + std::to_string(cr));
         return VA_OK;
@@ -462,7 +472,7 @@ void va_engine_destroy(va_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&e->slab, &e->partial, &e->ck_t, &e->ck_x, &e->own_accept, &e->own_reject, &e->own_status, &e->mu_tmp,
+    DevBuf *bufs[] = {&e->slab, &e->partial, &e->ck_t, &e->ck_x, &e->work_counter, &e->own_accept, &e->own_reject, &e->own_status, &e->mu_tmp,
                       &e->st_musum, &e->se_x0, &e->se_par, &e->se_xf, &e->se_lam, &e->se_mu, &e->se_acc, &e->se_rej, &e->se_sta};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < 2; ++s) {

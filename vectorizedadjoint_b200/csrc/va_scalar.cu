@@ -1,5 +1,7 @@
 // va_scalar.cu -- ahead-of-time instantiations of the thread-per-trajectory kernels (va_scalar_kernels.cuh) for the
 // built-in small systems: HarmonicOscillator and VanDerPol (N = 2, Npar = 1), all steppers.
+#include <algorithm>
+
 #include "va_common.cuh"
 #include "va_scalar_kernels.cuh"
 
@@ -42,7 +44,7 @@ template <class Sys, int S, bool FSAL>
 cudaError_t launch_forward(const VaScalarArgs &a, cudaStream_t st)
 {
     const int threads = 128;
-    const unsigned blocks = (unsigned)((a.B + threads - 1) / threads);
+    const unsigned blocks = (unsigned)std::min<int64_t>((a.B + threads - 1) / threads, a.grid_limit > 0 ? a.grid_limit : 148 * 4);
     if (a.adaptive) k_scalar_forward<Sys, S, FSAL, true><<<blocks, threads, 0, st>>>(a);
     else k_scalar_forward<Sys, S, FSAL, false><<<blocks, threads, 0, st>>>(a);
     return cudaGetLastError();
@@ -51,7 +53,7 @@ template <class Sys, int S>
 cudaError_t launch_adjoint(const VaScalarArgs &a, cudaStream_t st)
 {
     const int threads = 128;
-    const unsigned blocks = (unsigned)((a.B * a.n_out + threads - 1) / threads);
+    const unsigned blocks = (unsigned)std::min<int64_t>((a.B * a.n_out + threads - 1) / threads, a.grid_limit > 0 ? a.grid_limit : 148 * 4);
     k_scalar_adjoint<Sys, S><<<blocks, threads, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -71,23 +71,23 @@ __device__ __forceinline__ void rk_step(const VaTableau &tab, const double *x, c
     }
 }
 
+// Divergence control. Per-trajectory work varies widely (Van der Pol over three decades of mu: 6...600 accepted steps,
+// bursts of rejections), so lanes are NOT bound to trajectories: the grid is persistent, and a lane that finishes its
+// trajectory immediately fetches the next one from a global counter (work_counter). Every loop trip is one controller
+// attempt (one try_step) for every lane that has work, so a warp stays converged on the expensive code and idles only at
+// the very end of the batch. Checkpoints are addressed by trajectory index, so the reverse kernel can do the same.
 template <class Sys, int S, bool FSAL, bool ADAPTIVE>
 __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
 {
     constexpr int N = Sys::N, NPAR = Sys::NPAR;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
     const VaTableau &tab = a.tab;
-    double x[N], p[NPAR], K[S][N], xnew[N], xerr[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = a.x0[b * N + i];
-#pragma unroll
-    for (int k = 0; k < NPAR; ++k) p[k] = a.params[b * NPAR + k];
-
     const int64_t bs = a.arena_stride;
-    double t = a.ti, dt = a.dt0;
     const double tf = a.tf;
-    int nck = 0, count = 0, rejects = 0, status = 0;
+    double x[N], p[NPAR], K[S][N], xnew[N], xerr[N];
+    double t = 0.0, dt = 0.0;
+    int64_t b = -1;
+    int nck = 0, count = 0, rejects = 0, status = 0, trials = 0;
+    bool active = false, fresh = true, first_call = true;
 
     auto push = [&]() -> bool {
         if (nck > a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; return false; }
@@ -97,27 +97,48 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
         ++nck;
         return true;
     };
+    auto finalize = [&]() {
+        if (!status) push(); // the closing (t, x) entry: detail/runge_kutta.hpp:68-69, 113-115
+        bool finite = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) finite = finite && isfinite(x[i]);
+        if (!finite) status |= VA_TRAJ_NONFINITE;
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.x_final[b * N + i] = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS) ? nan("") : x[i];
+        a.n_accept[b] = count;
+        a.n_reject[b] = rejects;
+        a.status[b] = status;
+        active = false;
+    };
 
-    if (!ADAPTIVE) {
-        // detail/runge_kutta.hpp:51-71: t = ti + step*dt (no accumulation of dt)
-        while (va_less_eq_with_sign(t + dt, tf, dt)) {
-            if (!push()) break;
+    for (;;) {
+        if (!active) {
+            b = (int64_t)atomicAdd(a.work_counter, 1ULL);
+            if (b >= a.B) break;
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = a.x0[b * N + i];
+#pragma unroll
+            for (int k = 0; k < NPAR; ++k) p[k] = a.params[b * NPAR + k];
+            t = a.ti; dt = a.dt0;
+            nck = count = rejects = status = trials = 0;
+            fresh = first_call = true;
+            active = ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt);
+            if (!active) { finalize(); continue; }
+        }
+        if (!ADAPTIVE) {
+            // detail/runge_kutta.hpp:51-71: t = ti + step*dt (no accumulation of dt)
+            if (!push()) { finalize(); continue; }
             Sys::rhs(x, p, t, K[0]);
             rk_step<Sys, S, FSAL, false>(tab, x, p, t, dt, K, xnew, xerr);
 #pragma unroll
             for (int i = 0; i < N; ++i) x[i] = xnew[i];
             ++count;
             t = a.ti + (double)count * dt;
-        }
-        if (!status) push();
-    } else {
-        // detail/runge_kutta.hpp:92-117, one attempt (try_step) per loop trip so that lanes stay converged
-        bool active = va_less_with_sign(t, tf, dt);
-        bool fresh = true, first_call = true;
-        int trials = 0;
-        while (active) {
+            if (!va_less_eq_with_sign(t + dt, tf, dt)) finalize();
+        } else {
+            // detail/runge_kutta.hpp:92-117, one attempt (try_step) per loop trip
             if (fresh) {
-                if (!push()) break;
+                if (!push()) { finalize(); continue; }
                 if (va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
                 trials = 0;
                 fresh = false;
@@ -135,7 +156,7 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
                 // default_step_adjuster::decrease_step
                 dt *= fmax(0.9 * va_pow(err, -1.0 / ((double)tab.error_order - 1.0)), 0.2);
                 ++rejects;
-                if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; } // failed_step_checker
+                if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; finalize(); } // failed_step_checker
             } else {
                 t += dt;
 #pragma unroll
@@ -151,58 +172,65 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
                 }
                 ++count;
                 fresh = true;
-                active = va_less_with_sign(t, tf, dt);
+                if (!va_less_with_sign(t, tf, dt)) finalize();
             }
         }
-        if (!status) push();
     }
-    bool finite = true;
-#pragma unroll
-    for (int i = 0; i < N; ++i) finite = finite && isfinite(x[i]);
-    if (!finite) status |= VA_TRAJ_NONFINITE;
-#pragma unroll
-    for (int i = 0; i < N; ++i) a.x_final[b * N + i] = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS) ? nan("") : x[i];
-    a.n_accept[b] = count;
-    a.n_reject[b] = rejects;
-    a.status[b] = status;
 }
 
-// One thread per (trajectory, cost function).
+// One work item per (trajectory, cost function), fetched dynamically like in the forward kernel; one accepted step of
+// the reverse recursion per loop trip.
 template <class Sys, int S>
 __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
 {
     constexpr int N = Sys::N, NPAR = Sys::NPAR;
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = a.B * a.n_out;
-    if (w >= total) return;
-    // cost function index slowest: neighbouring lanes read neighbouring trajectories' checkpoints
-    const int o = (int)(w / a.B);
-    const int64_t b = w - (int64_t)o * a.B;
     const VaTableau &tab = a.tab;
     const int64_t bs = a.arena_stride;
-    double *lam_io = a.lambda + (b * a.n_out + o) * N;
-    double *mu_out = a.mu + (b * a.n_out + o) * NPAR;
-
     double p[NPAR], lam[N], mu[NPAR];
-#pragma unroll
-    for (int k = 0; k < NPAR; ++k) { p[k] = a.params[b * NPAR + k]; mu[k] = 0.0; }
-    if (a.status[b] & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS)) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) lam_io[i] = nan("");
-#pragma unroll
-        for (int k = 0; k < NPAR; ++k) mu_out[k] = nan("");
-        return;
-    }
-    const int T = a.n_accept[b];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        if (a.objective == VA_OBJ_SUM) lam[i] = 1.0;
-        else if (a.objective == VA_OBJ_HALF_NORM2) lam[i] = a.x_final[b * N + i];
-        else lam[i] = lam_io[i];
-    }
     double K[S][N], W[S + 1][N], u[N], xm[N], gx[N];
-    double t_next = a.ck_t[(int64_t)T * bs + b];
-    for (int n = T - 1; n >= 0; --n) {
+    double t_next = 0.0;
+    int64_t b = 0;
+    double *lam_io = nullptr, *mu_out = nullptr;
+    int n = -1;
+    bool have = false;
+    for (;;) {
+        if (n < 0) {
+            if (have) { // write back the finished work item
+#pragma unroll
+                for (int i = 0; i < N; ++i) lam_io[i] = lam[i];
+#pragma unroll
+                for (int k = 0; k < NPAR; ++k) mu_out[k] = mu[k];
+                have = false;
+            }
+            const int64_t w = (int64_t)atomicAdd(a.work_counter + 1, 1ULL);
+            if (w >= total) break;
+            // cost function index slowest: neighbouring items are neighbouring trajectories' checkpoints
+            const int o = (int)(w / a.B);
+            b = w - (int64_t)o * a.B;
+            lam_io = a.lambda + (b * a.n_out + o) * N;
+            mu_out = a.mu + (b * a.n_out + o) * NPAR;
+#pragma unroll
+            for (int k = 0; k < NPAR; ++k) { p[k] = a.params[b * NPAR + k]; mu[k] = 0.0; }
+            if (a.status[b] & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS)) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) lam_io[i] = nan("");
+#pragma unroll
+                for (int k = 0; k < NPAR; ++k) mu_out[k] = nan("");
+                continue;
+            }
+            const int T = a.n_accept[b];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (a.objective == VA_OBJ_SUM) lam[i] = 1.0;
+                else if (a.objective == VA_OBJ_HALF_NORM2) lam[i] = a.x_final[b * N + i];
+                else lam[i] = lam_io[i];
+            }
+            t_next = a.ck_t[(int64_t)T * bs + b];
+            n = T - 1;
+            have = true;
+            if (n < 0) continue;
+        }
         const double time = a.ck_t[(int64_t)n * bs + b];
         const double dt = t_next - time; // StateStorage::GetDt: difference of stored times
         t_next = time;
@@ -245,13 +273,9 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) lam[i] = W[0][i];
+        --n;
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) lam_io[i] = lam[i];
-#pragma unroll
-    for (int k = 0; k < NPAR; ++k) mu_out[k] = mu[k];
 }
-
 
 template <class Sys, int S, bool FSAL, bool ADAPTIVE>
 __global__ void __launch_bounds__(128) k_scalar_forward(const __grid_constant__ VaScalarArgs a)

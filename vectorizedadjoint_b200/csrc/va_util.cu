@@ -1,5 +1,7 @@
 // va_util.cu -- small support kernels: deterministic row reduction, the seeded synthetic-input generator and the two
 // microbenchmarks that give the roofline denominators (FP64 DFMA peak, HBM copy bandwidth) on the device at hand.
+#include <algorithm>
+
 #include "va_common.cuh"
 
 namespace {
@@ -119,12 +121,60 @@ __global__ void k_copy(const double4 *__restrict__ in, double4 *__restrict__ out
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
+// Stage 1 of the row reduction for tall inputs: block c sums rows [c*rpb, (c+1)*rpb) into part[c][k]. Thread = (k lane,
+// row lane): 32 consecutive k per warp (coalesced), 8 row lanes per block combined in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256) k_reduce_rows_stage(const double *__restrict__ in, int64_t G, int64_t stride, int64_t n,
+                                                           double *__restrict__ part, int64_t rpb)
+{
+    __shared__ double sm[8][33];
+    const int kl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rpb, r1 = r0 + rpb < G ? r0 + rpb : G;
+    for (int64_t kb = (int64_t)blockIdx.y * 32; kb < n; kb += (int64_t)gridDim.y * 32) {
+        const int64_t k = kb + kl;
+        double s = 0.0;
+        if (k < n)
+            for (int64_t r = r0 + rl; r < r1; r += 8) s += in[r * stride + k];
+        sm[rl][kl] = s;
+        __syncthreads();
+        if (rl == 0 && k < n) {
+            double t = sm[0][kl];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) t += sm[q][kl];
+            part[(int64_t)blockIdx.x * n + k] = t;
+        }
+        __syncthreads();
+    }
+}
+
 } // namespace
 
 cudaError_t va_reduce_rows(const double *in, int64_t G, int64_t stride, int64_t n, double *out, int accumulate, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const int threads = 128;
+    if (G > 4096) {
+        // tall: two stages through a scratch buffer (kept for the life of the process, grown on demand)
+        static double *scratch_dev[16] = {nullptr};
+        static size_t scratch_elems_dev[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        double *&scratch = scratch_dev[dev & 15];
+        size_t &scratch_elems = scratch_elems_dev[dev & 15];
+        const int64_t chunks = 1024, rpb = (G + chunks - 1) / chunks;
+        const int64_t used = (G + rpb - 1) / rpb;
+        if ((size_t)(used * n) > scratch_elems) {
+            if (scratch) cudaFree(scratch);
+            scratch = nullptr;
+            scratch_elems = 0;
+            cudaError_t e = cudaMalloc(&scratch, (size_t)(used * n) * 8);
+            if (e != cudaSuccess) return e;
+            scratch_elems = (size_t)(used * n);
+        }
+        const unsigned gy = (unsigned)std::min<int64_t>((n + 31) / 32, 64);
+        k_reduce_rows_stage<<<dim3((unsigned)used, gy), 256, 0, st>>>(in, G, stride, n, scratch, rpb);
+        k_reduce_rows<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(scratch, used, n, n, out, accumulate);
+        return cudaGetLastError();
+    }
     k_reduce_rows<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(in, G, stride, n, out, accumulate);
     return cudaGetLastError();
 }
