@@ -28,6 +28,7 @@ struct VaGlvWideArgs {
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);
+int va_glv_wide_pair();                            // trajectories a slot integrates forward together (slabs per slot)
 int va_glv_wide_padded(int n);                      // padded species count the kernel runs with (16, 32 or 64)
 int va_glv_wide_block_doubles(int n, int stepper); // step block: [8-double header (t_n) | X_0..X_{s-1} | g_0..g_{s-1}], padded width
 cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);

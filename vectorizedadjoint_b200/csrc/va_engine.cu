@@ -78,7 +78,7 @@ struct va_engine {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // wide family
-    int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1; // tpc: trajectories (slots) per CTA
+    int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -108,7 +108,7 @@ int64_t per_traj_arena_bytes(const va_engine *e) { return (int64_t)(e->cap + 1) 
 int ensure_workspace(va_engine *e, int64_t B)
 {
     if (is_glv(e)) {
-        const size_t need = (size_t)e->grid * e->tpc * e->slab_stride * 8;
+        const size_t need = (size_t)e->grid * e->tpc * e->pair * e->slab_stride * 8;
         if (int rc = e->slab.ensure(need)) return rc;
         if (int rc = e->partial.ensure((size_t)e->grid * e->tpc * e->desc.n_par * 8)) return rc;
         e->workspace_bytes = (int64_t)(e->slab.bytes + e->partial.bytes);
@@ -449,6 +449,7 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
     } else if (family == FAM_GLV_WIDE) {
         cudaError_t ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
+        e->pair = va_glv_wide_pair();
         if (ce != cudaSuccess) return bail(VA_E_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(ce));
         e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
         e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
@@ -644,7 +645,7 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     } else {
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
-        const double *base = e->slab.as<double>() + b * e->slab_stride;
+        const double *base = e->slab.as<double>() + b * e->pair * e->slab_stride; // first wave: trajectory b = slot b, slab 0
         const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE ? va_glv_wide_block_doubles(n, e->desc.stepper)
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));

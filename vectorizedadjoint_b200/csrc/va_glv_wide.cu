@@ -38,6 +38,9 @@
 #ifndef VA_GLV_LG
 #define VA_GLV_LG 8
 #endif
+#ifndef VA_GLV_PAIR
+#define VA_GLV_PAIR 1 // trajectories integrated forward together per slot
+#endif
 #ifndef VA_GLV_MINB
 #define VA_GLV_MINB 2 // resident CTAs per SM the register allocation is sized for
 #endif
@@ -129,15 +132,15 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
     constexpr int BLK = block_doubles<Tab, NP>();
-    __shared__ __align__(16) double xs_all[TPC][2][NP];   // stage state (forward) / v = w o x (backward), double buffered
+    __shared__ __align__(16) double xs_all[TPC][VA_GLV_PAIR][2][NP]; // stage state (forward, per paired trajectory) / v = w o x (backward)
     __shared__ __align__(128) double xg_all[TPC][2][BLK]; // step blocks [hdr | X_0..X_{s-1} | g_0..g_{s-1}] streamed back by TMA
-    __shared__ double red_all[TPC][NW > 0 ? NW : 1];
+    __shared__ double red_all[TPC][VA_GLV_PAIR * (NW > 0 ? NW : 1)];
     __shared__ __align__(8) uint64_t mbar_all[TPC][2];
     __shared__ int red_i_all[TPC][NW > 0 ? NW : 1];
 
     const int slot = threadIdx.x / NTT;
     const int tid = threadIdx.x % NTT; // thread index inside the trajectory group
-    double(*xs)[NP] = xs_all[slot];
+    double(*xs)[2][NP] = xs_all[slot];
     double(*xg)[BLK] = xg_all[slot];
     double *red = red_all[slot];
     uint64_t *mbar = mbar_all[slot];
@@ -152,7 +155,6 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
     const int npar = n * n + n;
     const int cap = a.cap;
     const int64_t gslot = (int64_t)blockIdx.x * TPC + slot; // global slot: owns one slab and one partial-sum row
-    double *const slab = a.slab + gslot * a.slab_stride;
 
     // barrier over the threads of ONE trajectory: a warp sync when a trajectory is a single warp, else a named barrier
     auto traj_sync = [&]() {
@@ -192,14 +194,25 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
 #pragma unroll
         for (int c = 0; c < 4; ++c) Abar[r][c] = 0.0;
 
-    for (int64_t b = gslot; b < a.B; b += (int64_t)gridDim.x * TPC) {
-        const double *pb = a.params + b * npar;
-
-        // ================================ forward sweep =====================================
-        // forward tile: 4 rows 4hi + k (held permuted: register k <- row R^k), TG columns FG(c)
-        double Af[4][TG];
-        double r_own = 0.0, x = 0.0;
-        {
+    // NQ trajectories are integrated FORWARD together, interleaved in the same warps: their matrix tiles sit side by side
+    // in the register file (the gradient accumulator is not live yet), every stage does NQ independent matrix-vector
+    // products behind ONE barrier, and the compiler overlaps the shuffle/LDS latency of one trajectory with the DFMAs of
+    // the other. The reverse sweeps then run one after the other (each needs A and Abar: 128 registers).
+    constexpr int NQ = VA_GLV_PAIR;
+    const int64_t wave = (int64_t)gridDim.x * TPC; // trajectories taken per wave of slots
+    for (int64_t b0 = gslot; b0 < a.B; b0 += wave * NQ) {
+        int64_t bq[NQ];
+        bool ex[NQ];
+        double Af[NQ][4][TG];
+        double r_own[NQ], x[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            bq[q] = b0 + q * wave;
+            ex[q] = bq[q] < a.B;
+            r_own[q] = 0.0;
+            x[q] = 0.0;
+            const double *pb = a.params + (ex[q] ? bq[q] : b0) * npar;
+            // forward tile: 4 rows 4hi + k (held permuted: register k <- row R^k), TG columns FG(c)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int row = 4 * hi + r;
@@ -208,191 +221,283 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
 #pragma unroll
                     for (int j = 0; j < TG / 2; ++j) {
                         const double2 v = __ldg(src + LG * j);
-                        Af[r][2 * j] = v.x;
-                        Af[r][2 * j + 1] = v.y;
+                        Af[q][r][2 * j] = v.x;
+                        Af[q][r][2 * j + 1] = v.y;
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < TG; ++c) {
                         const int col = FG(c);
-                        Af[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                        Af[q][r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
                     }
                 }
             }
 #pragma unroll
             for (int c = 0; c < TG; ++c) {
-                cswap(sw_lo, Af[0][c], Af[1][c]);
-                cswap(sw_lo, Af[2][c], Af[3][c]);
-                cswap(sw_hi, Af[0][c], Af[2][c]);
-                cswap(sw_hi, Af[1][c], Af[3][c]);
+                cswap(sw_lo, Af[q][0][c], Af[q][1][c]);
+                cswap(sw_lo, Af[q][2][c], Af[q][3][c]);
+                cswap(sw_hi, Af[q][0][c], Af[q][2][c]);
+                cswap(sw_hi, Af[q][1][c], Af[q][3][c]);
             }
-            if (own < n) { r_own = __ldg(pb + own); x = __ldg(a.x0 + b * n + own); }
+            if (ex[q] && own < n) { r_own[q] = __ldg(pb + own); x[q] = __ldg(a.x0 + bq[q] * n + own); }
         }
 
-        // sum = (A X)_own for the stage state whose own-component is X. `extra` runs between the operand loads and
-        // the reduction: work that does not depend on the result is issued there, off the critical path.
-        auto matvec = [&](double X, int m, auto &&extra) -> double { // m is a compile-time constant after unrolling
-            double *buf = xs[m & 1];
-            if (writer) buf[own] = X;
+        // sum[q] = (A_q X_q)_own for the stage states whose own-components are X[q]. `extra` runs between the operand
+        // loads and the reductions: work that does not depend on the results is issued there, off the critical path.
+        auto matvec = [&](const double(&X)[NQ], int m, double(&sum)[NQ], auto &&extra) { // m: compile-time after unrolling
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (writer) xs[q][m & 1][own] = X[q];
             traj_sync();
-            const double2 *xv = reinterpret_cast<const double2 *>(buf) + g;
-            double xc[TG];
+            double s[NQ][4];
 #pragma unroll
-            for (int j = 0; j < TG / 2; ++j) {
-                const double2 v = xv[LG * j];
-                xc[2 * j] = v.x;
-                xc[2 * j + 1] = v.y;
+            for (int q = 0; q < NQ; ++q) {
+                const double2 *xv = reinterpret_cast<const double2 *>(xs[q][m & 1]) + g;
+                double xc[TG];
+#pragma unroll
+                for (int j = 0; j < TG / 2; ++j) {
+                    const double2 v = xv[LG * j];
+                    xc[2 * j] = v.x;
+                    xc[2 * j + 1] = v.y;
+                }
+                if (NQ == 1) {
+                    // a single trajectory: two accumulator chains per tile row keep the FP64 pipe busy from one warp
+                    double u[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { s[q][r] = Af[q][r][0] * xc[0]; u[r] = Af[q][r][TG / 2] * xc[TG / 2]; }
+#pragma unroll
+                    for (int c = 1; c < TG / 2; ++c)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            s[q][r] = fma(Af[q][r][c], xc[c], s[q][r]);
+                            u[r] = fma(Af[q][r][TG / 2 + c], xc[TG / 2 + c], u[r]);
+                        }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) s[q][r] += u[r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) s[q][r] = Af[q][r][0] * xc[0];
+#pragma unroll
+                    for (int c = 1; c < TG; ++c)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) s[q][r] = fma(Af[q][r][c], xc[c], s[q][r]);
+                }
             }
-            // 8 independent accumulator chains (two per tile row) keep the FP64 pipe busy from a single warp
-            double s[4], u[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { s[r] = Af[r][0] * xc[0]; u[r] = Af[r][TG / 2] * xc[TG / 2]; }
-#pragma unroll
-            for (int c = 1; c < TG / 2; ++c)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { s[r] = fma(Af[r][c], xc[c], s[r]); u[r] = fma(Af[r][TG / 2 + c], xc[TG / 2 + c], u[r]); }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) s[r] += u[r];
             extra();
-            return reduce_group<LG>(s[0], s[1], s[2], s[3]);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sum[q] = reduce_group<LG>(s[q][0], s[q][1], s[q][2], s[q][3]);
         };
 
-        double t = a.ti, dt = a.dt0;
         const double tf = a.tf;
-        int nck = 0, rejects = 0, status = 0;
-        double K[S];
-        double g0 = r_own + matvec(x, 0, [] {});
-        K[0] = x * g0;
-
-        double *sp = slab + HDR + own; // this lane's column in the current step block (advanced on acceptance)
-        auto store_stage = [&](int m, double X, double gg) {
-            if (writer) {
-                sp[m * NP] = X;
-                sp[(SADJ + m) * NP] = gg;
+        double t[NQ], dt[NQ], K[NQ][S], g0[NQ];
+        int nck[NQ], rejects[NQ], status[NQ], trials[NQ];
+        bool act[NQ], fresh[NQ];
+        double *sp[NQ]; // this lane's column in the current step block of trajectory q (advanced on acceptance)
+        {
+            double sum[NQ];
+            matvec(x, 0, sum, [] {});
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                g0[q] = r_own[q] + sum[q];
+                K[q][0] = x[q] * g0[q];
+                t[q] = a.ti;
+                dt[q] = a.dt0;
+                nck[q] = rejects[q] = status[q] = trials[q] = 0;
+                fresh[q] = true;
+                act[q] = ex[q] && (ADAPTIVE ? va_less_with_sign(t[q], tf, dt[q]) : va_less_eq_with_sign(t[q] + dt[q], tf, dt[q]));
+                sp[q] = a.slab + (gslot * NQ + q) * a.slab_stride + HDR + own;
+            }
+        }
+        auto store_stage = [&](int q, int m, double X, double gg) {
+            if (writer && act[q]) {
+                sp[q][m * NP] = X;
+                sp[q][(SADJ + m) * NP] = gg;
             }
         };
+        auto any_active = [&]() {
+            bool r = false;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) r = r || act[q];
+            return r;
+        };
 
-        bool active = ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt);
-        bool fresh = true;
-        int trials = 0;
-        while (active) {
-            if (fresh) {
-                if (nck >= cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
-                store_stage(0, x, g0);
-                if (tid == 0) sp[-HDR] = t; // own == 0 for thread 0: header of the current block
-                if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
-                trials = 0;
-                fresh = false;
+        while (any_active()) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (act[q] && fresh[q]) {
+                    if (nck[q] >= cap) {
+                        status[q] |= VA_TRAJ_CKPT_OVERFLOW;
+                        act[q] = false;
+                    } else {
+                        store_stage(q, 0, x[q], g0[q]);
+                        if (tid == 0) sp[q][-HDR] = t[q]; // own == 0 for thread 0: header of the current block
+                        if (ADAPTIVE && va_less_with_sign(tf, t[q] + dt[q], dt[q])) dt[q] = tf - t[q];
+                        trials[q] = 0;
+                        fresh[q] = false;
+                    }
+                }
             }
+            if (!any_active()) break;
             // Stage m produces K_m = X_m (r + A X_m). The state of the NEXT stage (or the new solution after the last
             // one), Y = x + dt sum_{j<=m} c_j K_j, is split so that only ONE DFMA follows the reduction:
             //   Y = fma(c1, sum, base),  c1 = dt c_m X_m,  base = x + dt sum_{j<m} c_j K_j + c1 r   (all known early).
-            double X = fma(dt * a.coef.a[1][0], K[0], x);
-            double perr = 0.0; // sum_{j<SE-1} db_j K_j
+            double X[NQ], perr[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                X[q] = fma(dt[q] * a.coef.a[1][0], K[q][0], x[q]);
+                perr[q] = 0.0; // sum_{j<SE-1} db_j K_j
+            }
 #pragma unroll
             for (int m = 1; m < SE; ++m) {
                 const bool last = (m == SE - 1);
-                double c1 = 0.0, base = 0.0;
-                const double sum = matvec(X, m, [&] {
-                    double acc = 0.0;
+                double c1[NQ], base[NQ], sum[NQ];
+                matvec(X, m, sum, [&] {
 #pragma unroll
-                    for (int j = 0; j < m; ++j) {
-                        const double cz = last ? Tab::b(j) : Tab::a(m + 1, j);
-                        if (cz != 0.0) acc = fma(last ? a.coef.b[j] : a.coef.a[m + 1][j], K[j], acc);
-                    }
-                    const double cm = last ? Tab::b(m) : Tab::a(m + 1, m);
-                    c1 = (cm != 0.0) ? (dt * (last ? a.coef.b[m] : a.coef.a[m + 1][m])) * X : 0.0;
-                    base = fma(c1, r_own, fma(dt, acc, x));
-                    if (last && ADAPTIVE) {
+                    for (int q = 0; q < NQ; ++q) {
+                        double acc = 0.0;
 #pragma unroll
-                        for (int j = 0; j < m; ++j)
-                            if (Tab::db(j) != 0.0) perr = fma(a.coef.db[j], K[j], perr);
+                        for (int j = 0; j < m; ++j) {
+                            const double cz = last ? Tab::b(j) : Tab::a(m + 1, j);
+                            if (cz != 0.0) acc = fma(last ? a.coef.b[j] : a.coef.a[m + 1][j], K[q][j], acc);
+                        }
+                        const double cm = last ? Tab::b(m) : Tab::a(m + 1, m);
+                        c1[q] = (cm != 0.0) ? (dt[q] * (last ? a.coef.b[m] : a.coef.a[m + 1][m])) * X[q] : 0.0;
+                        base[q] = fma(c1[q], r_own[q], fma(dt[q], acc, x[q]));
+                        if (last && ADAPTIVE) {
+#pragma unroll
+                            for (int j = 0; j < m; ++j)
+                                if (Tab::db(j) != 0.0) perr[q] = fma(a.coef.db[j], K[q][j], perr[q]);
+                        }
                     }
                 });
-                const double Y = fma(c1, sum, base);
-                const double gg = r_own + sum;
-                K[m] = X * gg;
-                if (m < SADJ) store_stage(m, X, gg);
-                X = Y;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const double Y = fma(c1[q], sum[q], base[q]);
+                    const double gg = r_own[q] + sum[q];
+                    K[q][m] = X[q] * gg;
+                    if (m < SADJ) store_stage(q, m, X[q], gg);
+                    X[q] = Y;
+                }
             }
-            const double xnew = X;
-            double g_last = 0.0;
-            if (Tab::FSAL) {
-                g_last = r_own + matvec(xnew, S - 1, [] {});
-                K[S - 1] = xnew * g_last;
+            // X = new solution. f(xnew) is evaluated now for every trajectory: it is the FSAL stage of dopri5, and for the
+            // other steppers the first slope of the next step (speculative: discarded if the step is rejected).
+            double gl[NQ], Kl[NQ];
+            {
+                double sum[NQ];
+                matvec(X, SE & 1 ? 1 : 0, sum, [] {});
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    gl[q] = r_own[q] + sum[q];
+                    Kl[q] = X[q] * gl[q];
+                    if (Tab::FSAL) K[q][S - 1] = Kl[q];
+                }
             }
-            bool accept = true;
-            double err = 0.0;
+            double err[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) err[q] = 0.0;
             if (ADAPTIVE) {
-                double acc = perr;
+                double e[NQ];
 #pragma unroll
-                for (int j = SE - 1; j < S; ++j)
-                    if (Tab::db(j) != 0.0) acc = fma(a.coef.db[j], K[j], acc);
-                const double xerr = dt * acc;
-                // default_error_checker::error, max norm over species
-                double e = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
+                for (int q = 0; q < NQ; ++q) {
+                    double acc = perr[q];
 #pragma unroll
-                for (int d = 16; d >= LG / 4; d >>= 1) e = fmax(e, shfl_xor_d(e, d));
+                    for (int j = SE - 1; j < S; ++j)
+                        if (Tab::db(j) != 0.0) acc = fma(a.coef.db[j], K[q][j], acc);
+                    const double xerr = dt[q] * acc;
+                    // default_error_checker::error, max norm over species
+                    e[q] = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x[q]) + fabs(dt[q]) * fabs(K[q][0])));
+#pragma unroll
+                    for (int d = 16; d >= LG / 4; d >>= 1) e[q] = fmax(e[q], shfl_xor_d(e[q], d));
+                }
                 if (NW > 1) {
-                    if (lane == 0) red[warp] = e;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        if (lane == 0) red[q * NW + warp] = e[q];
                     traj_sync();
 #pragma unroll
-                    for (int w = 0; w < NW; ++w) err = fmax(err, red[w]);
-                } else {
-                    err = e;
-                }
-                accept = !(err > 1.0);
-            }
-            if (!accept) {
-                // default_step_adjuster::decrease_step
-                dt *= fmax(0.9 * inv_root<(Tab::ERROR_ORDER > 1 ? Tab::ERROR_ORDER - 1 : 1)>(err), 0.2);
-                ++rejects;
-                if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; }
-            } else {
-                x = xnew;
-                ++nck;
-                sp += BLK;
-                if (ADAPTIVE) {
-                    t += dt;
-                    // default_step_adjuster::increase_step
-                    if (err < 0.5) {
-                        constexpr int P = Tab::STEPPER_ORDER;
-                        double floor_ = 1.0;
+                    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                        for (int k = 0; k < P; ++k) floor_ *= 0.2; // 5^-P
-                        // err <= 5^-P: the growth factor is exactly 0.9 * 5 (pow(5^-P, -1/P) == 5 in glibc as well)
-                        dt *= (err <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root<P>(err);
-                    }
-                    active = va_less_with_sign(t, tf, dt);
+                        for (int w = 0; w < NW; ++w) err[q] = fmax(err[q], red[q * NW + w]);
                 } else {
-                    t = a.ti + (double)nck * dt; // detail/runge_kutta.hpp:64
-                    active = va_less_eq_with_sign(t + dt, tf, dt);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) err[q] = e[q];
                 }
-                fresh = true;
-                if (Tab::FSAL) {
-                    g0 = g_last;
-                    K[0] = K[S - 1];
-                } else if (active) {
-                    g0 = r_own + matvec(x, 0, [] {});
-                    K[0] = x * g0;
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (!act[q]) continue;
+                const bool accept = !ADAPTIVE || !(err[q] > 1.0);
+                if (!accept) {
+                    // default_step_adjuster::decrease_step
+                    dt[q] *= fmax(0.9 * inv_root<(Tab::ERROR_ORDER > 1 ? Tab::ERROR_ORDER - 1 : 1)>(err[q]), 0.2);
+                    ++rejects[q];
+                    if (++trials[q] >= 500) { status[q] |= VA_TRAJ_NO_PROGRESS; act[q] = false; }
+                } else {
+                    x[q] = X[q];
+                    ++nck[q];
+                    sp[q] += BLK;
+                    if (ADAPTIVE) {
+                        t[q] += dt[q];
+                        // default_step_adjuster::increase_step
+                        if (err[q] < 0.5) {
+                            constexpr int P = Tab::STEPPER_ORDER;
+                            double floor_ = 1.0;
+#pragma unroll
+                            for (int k = 0; k < P; ++k) floor_ *= 0.2; // 5^-P
+                            // err <= 5^-P: the growth factor is exactly 0.9 * 5 (pow(5^-P, -1/P) == 5 in glibc as well)
+                            dt[q] *= (err[q] <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root<P>(err[q]);
+                        }
+                        act[q] = va_less_with_sign(t[q], tf, dt[q]);
+                    } else {
+                        t[q] = a.ti + (double)nck[q] * dt[q]; // detail/runge_kutta.hpp:64
+                        act[q] = va_less_eq_with_sign(t[q] + dt[q], tf, dt[q]);
+                    }
+                    fresh[q] = true;
+                    g0[q] = gl[q];
+                    K[q][0] = Kl[q];
                 }
             }
         }
-        const int T = nck;
-        if (tid == 0) sp[-HDR] = t; // header of block T carries the final time
-        if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
-        fence_proxy_async();               // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
-        traj_sync();
-        status = traj_or(status);
-        const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
-        if (writer && own < n) a.x_final[b * n + own] = failed ? nan("") : x;
-        if (tid == 0) {
-            if (a.n_accept) a.n_accept[b] = T;
-            if (a.n_reject) a.n_reject[b] = rejects;
-            if (a.status) a.status[b] = status;
+        // close the trajectories: final time, status, x(tf)
+        int Tq[NQ];
+        bool failedq[NQ];
+        double x_tfq[NQ], t_finalq[NQ];
+        int st_all = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            Tq[q] = nck[q];
+            if (tid == 0 && ex[q]) sp[q][-HDR] = t[q]; // header of block T carries the final time
+            if (!isfinite(x[q])) status[q] |= VA_TRAJ_NONFINITE;
+            st_all |= status[q] << (8 * q);
         }
-        const double x_tf = x, t_final = t;
+        fence_proxy_async(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
+        traj_sync();
+        st_all = traj_or(st_all);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            status[q] = (st_all >> (8 * q)) & 0xff;
+            failedq[q] = status[q] & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
+            x_tfq[q] = x[q];
+            t_finalq[q] = t[q];
+            if (ex[q]) {
+                if (writer && own < n) a.x_final[bq[q] * n + own] = failedq[q] ? nan("") : x[q];
+                if (tid == 0) {
+                    if (a.n_accept) a.n_accept[bq[q]] = Tq[q];
+                    if (a.n_reject) a.n_reject[bq[q]] = rejects[q];
+                    if (a.status) a.status[bq[q]] = status[q];
+                }
+            }
+        }
 
+#pragma unroll 1
+        for (int q = 0; q < NQ; ++q) {
+        if (!ex[q]) continue;
+        const int64_t b = bq[q];
+        const double *pb = a.params + b * npar;
+        double *const slab = a.slab + (gslot * NQ + q) * a.slab_stride;
+        const int T = Tq[q];
+        const bool failed = failedq[q];
+        const double x_tf = x_tfq[q], t_final = t_finalq[q];
         // ================================ reverse sweep =====================================
         // transposed tile: TG rows FG(r), 4 columns 4hi + k (held permuted: register k <- column R^k); the owned
         // component stays `own`. A is re-read (L2 hit).
@@ -467,7 +572,7 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
                 double v = W[SADJ] * blk[HDR + (SADJ - 1) * NP + own];
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
-                    double *vb = xs[m & 1];
+                    double *vb = xs[0][m & 1];
                     if (writer) vb[own] = v;
                     traj_sync();
                     if (m == SADJ && step > 0 && tid == 0) {
@@ -480,9 +585,9 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
                     double vr[TG];
 #pragma unroll
                     for (int j = 0; j < TG / 2; ++j) {
-                        const double2 q = vv2[LG * j];
-                        vr[2 * j] = q.x;
-                        vr[2 * j + 1] = q.y;
+                        const double2 vq = vv2[LG * j];
+                        vr[2 * j] = vq.x;
+                        vr[2 * j + 1] = vq.y;
                     }
                     const double2 x01 = xx2[0], x23 = xx2[1];
                     const double xc[4] = {x01.x, x01.y, x23.x, x23.y};
@@ -495,10 +600,6 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
                         for (int c = 0; c < 4; ++c) { s[c] = fma(Ab[r][c], vr[r], s[c]); u[c] = fma(Ab[TG / 2 + r][c], vr[TG / 2 + r], u[c]); }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) s[c] += u[c];
-#pragma unroll
-                    for (int r = 0; r < TG; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) Abar[r][c] = fma(vr[r], xc[c], Abar[r][c]);
                     // gx = (A^T v)_own + w_m g_{m-1}. The next stage's v = (w_{m-1} + gx a dt) X_{m-2} is arranged as
                     // fma(sum, c1, c2) with c1, c2 known before the reduction returns: one DFMA on the critical path.
                     const double wg = W[m] * blk[HDR + (SADJ + m - 1) * NP + own];
@@ -508,7 +609,26 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
                         if (Tab::a(m - 1, m - 2) != 0.0) c1 = (a.coef.a[m - 1][m - 2] * dt_s) * Xn;
                         c2 = fma(wg, c1, W[m - 1] * Xn);
                     }
-                    const double sum = reduce_group<LG>(s[0], s[1], s[2], s[3]);
+                    // first exchange round of the reduction is issued BEFORE the rank-1 gradient update: the 32 independent
+                    // Abar DFMAs (not on the critical path) then execute while the shuffles are in flight
+                    double k0 = s[0], k1 = s[1];
+                    const double e2 = shfl_xor_d(s[2], LG / 2), e3 = shfl_xor_d(s[3], LG / 2);
+#pragma unroll
+                    for (int r = 0; r < TG; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) Abar[r][c] = fma(vr[r], xc[c], Abar[r][c]);
+                    k0 += e2;
+                    k1 += e3;
+                    double sum;
+                    if (LG == 8) {
+                        const double a1 = shfl_xor_d(k0, 1), a2 = shfl_xor_d(k1, 2), a3 = shfl_xor_d(k1, 3);
+                        sum = (k0 + a1) + (a2 + a3);
+                    } else {
+                        k0 += shfl_xor_d(k1, LG / 4);
+#pragma unroll
+                        for (int d = LG / 8; d >= 1; d >>= 1) k0 += shfl_xor_d(k0, d);
+                        sum = k0;
+                    }
                     const double v_next = fma(sum, c1, c2);
                     const double gx = sum + wg;
                     const double gxd = gx * dt_s;
@@ -542,6 +662,7 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
             }
         }
         traj_sync(); // slab and shared buffers are reused by the next trajectory
+        } // q: reverse sweeps, one trajectory after the other
     }
 
     if (a.reduce == VA_REDUCE_SUM) {
@@ -627,6 +748,8 @@ bool va_glv_wide_supported(int n, int stepper, int adaptive)
 }
 
 int va_glv_wide_padded(int n) { return np_of(n); }
+
+int va_glv_wide_pair() { return VA_GLV_PAIR; }
 
 int va_glv_wide_block_doubles(int n, int stepper) { return HDR + 2 * sadj_of(stepper) * np_of(n); }
 
