@@ -1,7 +1,11 @@
-for P in 2 1; do
-  rm -f vectorizedadjoint_b200/csrc/build/va_glv_wide.o
-  make -s -C vectorizedadjoint_b200/csrc GLV_PAIR=$P -j8 > /dev/null
-  echo "== PAIR=$P"
-  timeout 600 python -m pytest tests -m gpu -q -k "glv" 2>&1 | tail -2
-  python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'])"
-done
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1_final.json 2>gpurun_out/bench_r1_final.err
+for w in glv16 vdp harmonic glv256; do python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/bench_r1_$w.json 2>>gpurun_out/bench_r1_final.err; done
+python bench.py --reduce none --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_r1_glv64_reduce_none.json 2>>gpurun_out/bench_r1_final.err
+python -c "
+import json,glob
+for f in sorted(glob.glob('gpurun_out/bench_r1_*.json')):
+    try:
+        d=json.load(open(f)); print(f, round(d['value']), round(d['ms_per_step'],2), d.get('roofline',{}).get('frac'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('value'))
+    except Exception as e: print(f, 'ERR', e)
+"
+tail -3 gpurun_out/bench_r1_final.err
