@@ -167,7 +167,7 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
                 }
                 // default_step_adjuster::increase_step
                 if (err < 0.5) {
-                    err = fmax(va_pow(5.0, -(double)tab.stepper_order), err);
+                    err = fmax(tab.growth_floor, err); // pow(5.0, -stepper_order)
                     dt *= 9.0 / 10.0 * va_pow(err, -1.0 / (double)tab.stepper_order);
                 }
                 ++count;

@@ -5,6 +5,7 @@
 // adds Dormand-Prince 5(4), which the reference's reverse pass does not know (ButcherTable.hpp:247-250).
 // Every coefficient is the correctly rounded quotient of two small integers, as in odeint; the embedded-error weights
 // are formed as (rounded b) - (rounded b-hat), also as odeint does.
+#include <cmath>
 #include <cstring>
 
 #include "va_common.cuh"
@@ -18,7 +19,16 @@ void fill_a(VaTableau *tb, const Frac *f, int count)
 }
 } // namespace
 
+static int fill(int kind, VaTableau *tb);
+
 int va_tableau_host(int kind, VaTableau *tb)
+{
+    const int rc = fill(kind, tb);
+    if (rc == 0) tb->growth_floor = std::pow(5.0, -(double)tb->stepper_order);
+    return rc;
+}
+
+static int fill(int kind, VaTableau *tb)
 {
     std::memset(tb, 0, sizeof(*tb));
     double *b = tb->b, *db = tb->db, *c = tb->c;

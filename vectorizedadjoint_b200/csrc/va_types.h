@@ -30,6 +30,8 @@ struct VaTableau {
     double b[VA_MAX_STAGES];
     double db[VA_MAX_STAGES];
     double c[VA_MAX_STAGES];
+    double growth_floor; // pow(5.0, -stepper_order), the error floor of default_step_adjuster::increase_step, evaluated once on
+                         // the host with the system pow() (what the reference evaluates at every accepted step)
 };
 
 // odeint util/detail/less_with_sign.hpp, as used by reference lib/include/detail/runge_kutta.hpp:55,93,98
