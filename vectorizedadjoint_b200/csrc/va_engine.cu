@@ -101,6 +101,8 @@ struct va_engine {
 
 namespace {
 
+int ck_layout_of(const va_engine *e) { return e->desc.adaptive ? 1 : 0; } // see va_scalar_kernels.cuh: ck_store
+
 bool is_glv(const va_engine *e) { return e->family == FAM_GLV_WIDE || e->family == FAM_GLV_STREAM; }
 
 int64_t per_traj_arena_bytes(const va_engine *e) { return (int64_t)(e->cap + 1) * (e->desc.n_state + 1) * 8; }
@@ -129,8 +131,12 @@ int ensure_workspace(va_engine *e, int64_t B)
     int64_t traj = std::min<int64_t>(B, std::max<int64_t>(1, budget / per));
     if (traj < B) traj = std::max<int64_t>(128, traj / 128 * 128); // whole CTAs per wave
     if (traj > e->arena_traj) {
-        if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * 8)) return rc;
-        if (int rc = e->ck_x.ensure((size_t)traj * (e->cap + 1) * e->desc.n_state * 8)) return rc;
+        if (ck_layout_of(e) == 1) {
+            if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * (e->desc.n_state + 1) * 8)) return rc;
+        } else {
+            if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * 8)) return rc;
+            if (int rc = e->ck_x.ensure((size_t)traj * (e->cap + 1) * e->desc.n_state * 8)) return rc;
+        }
         e->arena_traj = traj;
     }
     e->workspace_bytes = (int64_t)(e->ck_t.bytes + e->ck_x.bytes);
@@ -144,6 +150,7 @@ int scalar_forward(va_engine *e, const VaScalarArgs &a_in, cudaStream_t st)
     if (int rc = e->work_counter.ensure(16)) return rc;
     VA_CUDA(cudaMemsetAsync(e->work_counter.p, 0, 16, st));
     VaScalarArgs a = a_in;
+    a.ck_layout = ck_layout_of(e);
     a.work_counter = e->work_counter.as<unsigned long long>();
     a.grid_limit = e->sm_count * 16; // 16 x 128 threads = the most an SM can hold; surplus CTAs just find the queue empty
     if (e->family == FAM_TAPE) {
@@ -158,6 +165,7 @@ int scalar_adjoint(va_engine *e, const VaScalarArgs &a_in, cudaStream_t st)
     if (int rc = e->work_counter.ensure(16)) return rc;
     VA_CUDA(cudaMemsetAsync(e->work_counter.as<unsigned long long>() + 1, 0, 8, st));
     VaScalarArgs a = a_in;
+    a.ck_layout = ck_layout_of(e);
     a.work_counter = e->work_counter.as<unsigned long long>();
     a.grid_limit = e->sm_count * 16; // 16 x 128 threads = the most an SM can hold; surplus CTAs just find the queue empty
     if (e->family == FAM_TAPE) {
@@ -639,9 +647,16 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     if (capacity < T + 1) return fail(VA_E_INVALID, "capacity too small");
     VA_CUDA(cudaSetDevice(e->device));
     if (!is_glv(e)) {
-        const size_t pitch = (size_t)e->arena_traj * 8;
-        if (t) VA_CUDA(cudaMemcpy2D(t, 8, e->ck_t.as<double>() + b, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
-        if (x) VA_CUDA(cudaMemcpy2D(x, 8, e->ck_x.as<double>() + b, pitch, 8, (size_t)(T + 1) * n, cudaMemcpyDeviceToHost));
+        if (ck_layout_of(e) == 1) { // per-trajectory records {t, x}
+            const double *rec = e->ck_t.as<double>() + b * (int64_t)(e->cap + 1) * (n + 1);
+            const size_t pitch = (size_t)(n + 1) * 8;
+            if (t) VA_CUDA(cudaMemcpy2D(t, 8, rec, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
+            if (x) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, rec + 1, pitch, (size_t)n * 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
+        } else {
+            const size_t pitch = (size_t)e->arena_traj * 8;
+            if (t) VA_CUDA(cudaMemcpy2D(t, 8, e->ck_t.as<double>() + b, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
+            if (x) VA_CUDA(cudaMemcpy2D(x, 8, e->ck_x.as<double>() + b, pitch, 8, (size_t)(T + 1) * n, cudaMemcpyDeviceToHost));
+        }
     } else {
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).

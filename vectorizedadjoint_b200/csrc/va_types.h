@@ -64,6 +64,7 @@ struct VaScalarArgs {
     double *mu;                     // [B][n_out][NPAR]
     int32_t *n_accept, *n_reject, *status; // [B] (engine-owned or caller's)
     double *ck_t, *ck_x;
+    int ck_layout;                    // 0: t[n][b], x[n][i][b] (fixed step); 1: per-trajectory records {t, x} in ck_t (adaptive)
     unsigned long long *work_counter; // [2]: next trajectory (forward kernel), next work item (reverse kernel); zeroed per launch
     int grid_limit;                   // resident CTAs the persistent grid may use
 };
