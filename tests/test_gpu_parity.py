@@ -374,3 +374,45 @@ def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     assert_close(w["mu"][:, 0], s["mu"][:, 0], rtol=1e-11, what="mu")
     assert len(t) == f["n_accept"][3] + 1 and t[0] == 0.0
     np.testing.assert_array_equal(x[0], x0[3])
+
+
+def test_backward_in_time_integration(va):
+    """dt0 < 0 (tf < ti): odeint's less_with_sign logic is sign-aware (reference lib/include/detail/runge_kutta.hpp:93,98)."""
+    B = 64
+    p = np.minimum(oracle.synth_params(oracle.SYS_VANDERPOL, 2, 3, 0, B), 4.0)  # backward in time the stiff cases blow up
+    x0 = oracle.synth_x0(oracle.SYS_VANDERPOL, 2, p)
+    o = oracle.forward_adjoint(oracle.SYS_VANDERPOL, 2, oracle.RK_CK54, True, 1e-7, 1e-7, x0, p, 0.3, 0.0, -1e-3, objective=oracle.OBJ_SUM)
+    assert np.isfinite(o["x_final"]).all()
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_CK54, True, 1e-7, 1e-7, max_steps=4096) as e:
+        r = e.forward_adjoint(x0, p, 0.3, 0.0, -1e-3, objective=va.OBJ_SUM)
+    assert (r["status"] == 0).all()
+    np.testing.assert_array_equal(r["n_accept"], o["n_accept"])
+    np.testing.assert_array_equal(r["x_final"], o["x_final"])
+    assert_close(r["mu"][:, 0], o["mu"], rtol=1e-11, what="mu")
+    N = 16
+    pg = oracle.synth_params(oracle.SYS_GLV, N, 3, 0, 8)
+    xg = oracle.synth_x0(oracle.SYS_GLV, N, pg)
+    og = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, xg, pg, 0.2, 0.0, -1e-3, objective=oracle.OBJ_SUM)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        rg = e.forward_adjoint(xg, pg, 0.2, 0.0, -1e-3, objective=va.OBJ_SUM)
+    np.testing.assert_array_equal(rg["n_accept"], og["n_accept"])
+    assert_close(rg["x_final"], og["x_final"], what="x(tf)")
+    assert_close(rg["mu"][:, 0], og["mu"], what="mu")
+
+
+def test_no_progress_status_and_error_paths(va):
+    """A hopeless tolerance makes the controller reject 500 times: per-trajectory status, batch not aborted (reference:
+    odeint::no_progress_error from failed_step_checker, lib/include/detail/runge_kutta.hpp:85-86,106)."""
+    with pytest.raises(va.EngineError):
+        va.Engine(va.SYS_VANDERPOL, 2, 99, True, 1e-6, 1e-6)  # unknown stepper ("This ... stepper is not supported yet!")
+    with pytest.raises(va.EngineError):
+        va.Engine(va.SYS_VANDERPOL, 2, va.RK_RK4, True, 1e-6, 1e-6)  # rk4 has no error estimate: cannot be controlled
+    with pytest.raises(va.EngineError):
+        va.Engine(va.SYS_GLV, 8, va.RK_CK54, True, 1e-6, 1e-6, n_par=5)  # wrong parameter count
+    p = np.array([[1000.0], [1.0]])
+    x0 = oracle.synth_x0(oracle.SYS_VANDERPOL, 2, p)
+    with va.Engine(va.SYS_VANDERPOL, 2, va.RK_CK54, True, 1e-300, 0.0, max_steps=64) as e:
+        r = e.forward_adjoint(x0, p, 0.0, 0.5, 1e-3, objective=va.OBJ_SUM)
+    o = oracle.forward_adjoint(oracle.SYS_VANDERPOL, 2, oracle.RK_CK54, True, 1e-300, 0.0, x0, p, 0.0, 0.5, 1e-3, objective=oracle.OBJ_SUM)
+    np.testing.assert_array_equal(r["status"] & va.TRAJ_NO_PROGRESS != 0, o["status"] == 2)
+    assert (r["status"] != 0).all() and np.isnan(r["mu"]).all()
