@@ -354,6 +354,36 @@ def test_glv_large_species_counts_streamed_matrix(va, N, B, stepper, adaptive, t
     assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
 
 
+@pytest.mark.parametrize("N,B,stepper,adaptive,tol,tf,dt0", [(100, 5, 2, True, 1e-8, 10.0, 1e-3), (256, 2, 3, True, 1e-6, 10.0, 1e-3),
+                                                            (64, 6, 1, False, 0.0, 0.3, 0.01)])
+def test_glv_checkpoint_policy_recompute_matches_store_stages(va, N, B, stepper, adaptive, tol, tf, dt0):
+    """north_star item 4: the reverse sweep either reads stored stages or recomputes them from the stored (t_n, x_n)
+    (the reference's policy, detail/backpropagation.hpp:24-64). Both must give the reference's gradients; the recompute
+    policy keeps 8(N+8) B per step instead of 8(12N+8) B."""
+    p = oracle.synth_params(oracle.SYS_GLV, N, 77, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_SUM, threads=8)
+    res = {}
+    for pol in (va.CKPT_STORE_STAGES, va.CKPT_RECOMPUTE):
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, ckpt_policy=pol) as e:
+            info = e.info()
+            assert info["ckpt_policy"] == pol
+            if pol == va.CKPT_RECOMPUTE:
+                assert info["kernel_family"] == 2
+            res[pol] = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
+            e.forward(x0, p, 0.0, tf, dt0)
+            t, x = e.checkpoints(1)
+        r = res[pol]
+        assert (r["status"] == 0).all()
+        np.testing.assert_array_equal(r["n_accept"], o["n_accept"])
+        assert_close(r["x_final"], o["x_final"], what="x(tf)")
+        assert_close(r["lam"][:, 0], o["lam"], what="lambda")
+        assert_close(r["mu"][:, 0], o["mu"], what="mu")
+        assert len(t) == r["n_accept"][1] + 1 and t[0] == 0.0
+        np.testing.assert_array_equal(x[0], x0[1])
+    assert_close(res[va.CKPT_RECOMPUTE]["mu"], res[va.CKPT_STORE_STAGES]["mu"], rtol=1e-11, what="mu, recompute vs store")
+
+
 def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     """The two GLV kernel families are independent implementations: cross-check them at N = 64."""
     N, B = 64, 40

@@ -31,6 +31,7 @@ RK_EULER, RK_RK4, RK_CK54, RK_DOPRI5, RK_RKF78 = 0, 1, 2, 3, 4
 OBJ_SEED, OBJ_SUM, OBJ_HALF_NORM2 = 0, 1, 2
 REDUCE_NONE, REDUCE_SUM = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
+CKPT_AUTO, CKPT_RECOMPUTE, CKPT_STORE_STAGES = 0, 1, 2
 TRAJ_OK, TRAJ_CKPT_OVERFLOW, TRAJ_NO_PROGRESS, TRAJ_NONFINITE = 0, 1, 2, 4
 
 EXPORTS = ["va_engine_create", "va_engine_destroy", "va_engine_get_info", "va_last_error", "va_forward_batch", "va_adjoint_batch",
@@ -134,11 +135,12 @@ class Engine:
     """One engine = one ODE system + stepper + tolerances on one GPU (the reference's Driver, batched)."""
 
     def __init__(self, system: int, n_state: int, stepper: int, adaptive: bool, eps_abs: float = 0.0, eps_rel: float = 0.0,
-                 n_out: int = 1, device: int = 0, max_steps: int = 0, n_par: int | None = None, workspace_fraction: float = 0.0):
+                 n_out: int = 1, device: int = 0, max_steps: int = 0, n_par: int | None = None, workspace_fraction: float = 0.0,
+                 ckpt_policy: int = 0):
         self._h = ctypes.c_void_p()
         self.system, self.n, self.n_out = system, n_state, n_out
         self.npar = npar_of(system, n_state) if n_par is None else n_par
-        d = _Desc(system, n_state, self.npar, n_out, stepper, int(adaptive), eps_abs, eps_rel, device, max_steps, 0, 0,
+        d = _Desc(system, n_state, self.npar, n_out, stepper, int(adaptive), eps_abs, eps_rel, device, max_steps, ckpt_policy, 0,
                   workspace_fraction, None)
         _check(lib().va_engine_create(ctypes.byref(d), ctypes.byref(self._h)), "va_engine_create")
 

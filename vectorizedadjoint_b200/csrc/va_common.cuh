@@ -24,6 +24,8 @@ struct VaGlvWideArgs {
     int64_t slab_stride;
     double *partial;      // VA_REDUCE_SUM: [grid * slots per CTA][n_par] per-CTA partial sums (reduced by va_reduce_rows)
     int grid;
+    int blk_doubles;      // va_glv_t8.cu: doubles per step block (the v section is separate when n_out > 1)
+    int recompute;        // streamed family: 1 = keep only (t_n, x_n) and recompute the stages in the reverse sweep
     struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
@@ -34,9 +36,15 @@ int va_glv_wide_block_doubles(int n, int stepper); // step block: [8-double head
 cudaError_t va_glv_wide_config(int n, int stepper, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);
 cudaError_t va_glv_wide_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
+// second-generation register kernel for 33..64 species (va_glv_t8.cu): 64 threads per trajectory, 8x8 tiles, three phases
+bool va_glv_t8_supported(int n, int stepper, int adaptive);
+int va_glv_t8_block_doubles(int stepper, int n_out);
+cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads);
+cudaError_t va_glv_t8_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
 // streamed-matrix GLV family (va_glv_stream.cu): any N, one 256-thread CTA per trajectory, same argument block
 bool va_glv_stream_supported(int n, int stepper, int adaptive);
-int va_glv_stream_block_doubles(int n, int stepper);
+int va_glv_stream_block_doubles(int n, int stepper, int recompute);
 cudaError_t va_glv_stream_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
 // out[k] (+)= sum_{g<G} in[g*stride + k], deterministic order

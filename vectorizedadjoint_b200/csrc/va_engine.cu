@@ -79,6 +79,8 @@ struct va_engine {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // wide family
     int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
+    bool t8 = false;  // FAM_GLV_WIDE served by va_glv_t8.cu (33..64 species)
+    int glv_blk = 0;  // doubles per step block of the register-kernel slab
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -211,6 +213,8 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.n_accept = acc; a.n_reject = rej; a.status = sta;
         a.slab = e->slab.as<double>(); a.slab_stride = e->slab_stride; a.partial = e->partial.as<double>();
         a.grid = (int)std::min<int64_t>(e->grid, (d.B + e->tpc - 1) / e->tpc);
+        a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE;
+        a.blk_doubles = e->glv_blk;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
         if (sum && !native_sum && !d.forward_only) {
             // several cost functions per trajectory: per-trajectory gradients into a scratch buffer, then a row reduction
@@ -221,7 +225,8 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
             a.reduce = native_sum ? VA_REDUCE_SUM : VA_REDUCE_NONE;
             a.mu = d.mu;
         }
-        if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
+        if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
+        else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
         else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
         ++e->launches;
         if (native_sum) {
@@ -407,8 +412,9 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         break;
     case VA_SYS_GLV:
         if (desc->n_par != desc->n_state * desc->n_state + desc->n_state) return fail(VA_E_INVALID, "GLV: n_par must be N*N + N");
-        if (va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_FORCE_STREAM"))
-            family = FAM_GLV_WIDE; // N <= 64: matrix in registers
+        if (va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_FORCE_STREAM") &&
+            desc->ckpt_policy != VA_CKPT_RECOMPUTE)
+            family = FAM_GLV_WIDE; // N <= 64: matrix in registers (store-stages policy only)
         else if (va_glv_stream_supported(desc->n_state, desc->stepper, desc->adaptive))
             family = FAM_GLV_STREAM; // any N: matrix streamed from L2/HBM
         else
@@ -453,13 +459,34 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         e->grid = e->sm_count * e->ctas_per_sm;
         e->threads = 256;
         e->tpc = 1;
-        e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper);
-        e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
+        // checkpoint policy (north_star item 4): STORE_STAGES unless the caller asks for RECOMPUTE, or (AUTO) the slabs of
+        // all resident CTAs at the requested capacity would take more than the workspace share of free HBM
+        int policy = desc->ckpt_policy;
+        if (policy == VA_CKPT_AUTO) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const double frac = desc->workspace_fraction > 0 ? desc->workspace_fraction : 0.5;
+            const double need = (double)e->grid * (e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, 0) * 8.0;
+            policy = need > frac * (double)free_b ? VA_CKPT_RECOMPUTE : VA_CKPT_STORE_STAGES;
+        }
+        e->desc.ckpt_policy = policy;
+        e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, policy == VA_CKPT_RECOMPUTE);
     } else if (family == FAM_GLV_WIDE) {
-        cudaError_t ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
-        e->pair = va_glv_wide_pair();
+        // 33..64 species: second-generation kernel (va_glv_t8.cu); VA_GLV_V1 keeps the first generation for cross-checks
+        e->t8 = va_glv_t8_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_V1");
+        cudaError_t ce;
+        if (e->t8) {
+            ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads);
+            e->tpc = e->pair = 1;
+            e->glv_blk = va_glv_t8_block_doubles(desc->stepper, desc->n_out);
+            e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+        } else {
+            ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
+            e->pair = va_glv_wide_pair();
+            e->glv_blk = va_glv_wide_block_doubles(desc->n_state, desc->stepper);
+            e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
+        }
         if (ce != cudaSuccess) return bail(VA_E_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(ce));
-        e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
         e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
     } else {
         e->threads = 128;
@@ -661,8 +688,8 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
         const double *base = e->slab.as<double>() + b * e->pair * e->slab_stride; // first wave: trajectory b = slot b, slab 0
-        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE ? va_glv_wide_block_doubles(n, e->desc.stepper)
-                                                                : va_glv_stream_block_doubles(n, e->desc.stepper)) * 8;
+        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE ? e->glv_blk
+                                                                : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {
             if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + 8, pitch, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));

@@ -26,7 +26,10 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-template <class Tab, bool ADAPTIVE>
+// RECOMPUTE selects the checkpoint policy (north_star item 4): false = STORE_STAGES (stage states and slopes of every
+// accepted step are kept: 16 s N B per step), true = the reference's policy (only (t_n, x_n) is kept: 8 N B per step, the
+// stages are recomputed in the reverse sweep with s extra matrix-vector products, detail/backpropagation.hpp:24-64).
+template <class Tab, bool ADAPTIVE, bool RECOMPUTE>
 __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
@@ -34,9 +37,10 @@ __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGl
     extern __shared__ double sm[];
     const int n = a.n, npar = n * n + n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int BLK = 8 + 2 * SADJ * n;
+    const int BLK = RECOMPUTE ? 8 + n : 8 + 2 * SADJ * n;
     // shared vectors: x, xs (stage state), K[S], W[SADJ+1], v, gx, red
     double *x = sm, *xs = x + n, *K = xs + n, *W = K + S * n, *v = W + (SADJ + 1) * n, *gx = v + n, *g0 = gx + n, *red = g0 + n;
+    double *rXG = red + 64; // RECOMPUTE: recomputed stage states / slopes of the current step, [2][SADJ][n]
     __shared__ double s_scalar[4];
     double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
 
@@ -68,7 +72,10 @@ __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGl
             if (fresh) {
                 if (nck >= a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
                 __syncthreads();
-                for (int i = tid; i < n; i += SNT) { blk[8 + i] = x[i]; blk[8 + SADJ * n + i] = g0[i]; }
+                for (int i = tid; i < n; i += SNT) {
+                    blk[8 + i] = x[i];
+                    if (!RECOMPUTE) blk[8 + SADJ * n + i] = g0[i];
+                }
                 if (tid == 0) blk[0] = t;
                 if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
                 trials = 0;
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGl
                 matvec(xs, gx);
                 for (int i = tid; i < n; i += SNT) {
                     K[m * n + i] = xs[i] * gx[i];
-                    if (m < SADJ) { blk[8 + m * n + i] = xs[i]; blk[8 + (SADJ + m) * n + i] = gx[i]; }
+                    if (!RECOMPUTE && m < SADJ) { blk[8 + m * n + i] = xs[i]; blk[8 + (SADJ + m) * n + i] = gx[i]; }
                 }
             }
             __syncthreads();
@@ -192,6 +199,23 @@ __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGl
                 const double *blk = slab + (int64_t)step * BLK;
                 const double dt_s = t_hi - blk[0];
                 t_hi = blk[0];
+                if (RECOMPUTE) {
+                    // stage recompute from x_n with dt = t_{n+1} - t_n: X_m = x_n + dt sum_j a_mj K_j, g_m = r + A X_m
+                    double *rX = rXG, *rG = rXG + SADJ * n;
+#pragma unroll
+                    for (int m = 0; m < SADJ; ++m) {
+                        __syncthreads();
+                        for (int i = tid; i < n; i += SNT) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int j = 0; j < m; ++j)
+                                if (Tab::a(m, j) != 0.0) acc = fma(Tab::a(m, j), K[j * n + i], acc);
+                            rX[m * n + i] = fma(dt_s, acc, blk[8 + i]);
+                        }
+                        matvec(rX + m * n, rG + m * n);
+                        for (int i = tid; i < n; i += SNT) K[m * n + i] = rX[m * n + i] * rG[m * n + i];
+                    }
+                }
                 __syncthreads();
                 for (int i = tid; i < n; i += SNT) {
                     W[i] = lam[i];
@@ -200,7 +224,8 @@ __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGl
                 }
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
-                    const double *X = blk + 8 + (m - 1) * n, *G = blk + 8 + (SADJ + m - 1) * n;
+                    const double *X = RECOMPUTE ? rXG + (m - 1) * n : blk + 8 + (m - 1) * n;
+                    const double *G = RECOMPUTE ? rXG + (SADJ + m - 1) * n : blk + 8 + (SADJ + m - 1) * n;
                     __syncthreads();
                     for (int i = tid; i < n; i += SNT) v[i] = W[m * n + i] * X[i];
                     __syncthreads();
@@ -235,13 +260,18 @@ __global__ void __launch_bounds__(SNT) k_glv_stream(const __grid_constant__ VaGl
     (void)s_scalar;
 }
 
+template <class Tab, bool ADAPTIVE, bool RECOMPUTE>
+cudaError_t launch2(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_glv_stream<Tab, ADAPTIVE, RECOMPUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_glv_stream<Tab, ADAPTIVE, RECOMPUTE><<<a.grid, SNT, smem, st>>>(a);
+    return cudaGetLastError();
+}
 template <class Tab, bool ADAPTIVE>
 cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_glv_stream<Tab, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_glv_stream<Tab, ADAPTIVE><<<a.grid, SNT, smem, st>>>(a);
-    return cudaGetLastError();
+    return a.recompute ? launch2<Tab, ADAPTIVE, true>(a, st, smem) : launch2<Tab, ADAPTIVE, false>(a, st, smem);
 }
 
 int stages_of(int stepper, int *sadj)
@@ -257,33 +287,33 @@ int stages_of(int stepper, int *sadj)
 
 } // namespace
 
-size_t va_glv_stream_smem(int n, int stepper)
+size_t va_glv_stream_smem(int n, int stepper, int recompute)
 {
     int sadj = 0;
     const int s = stages_of(stepper, &sadj);
-    return (size_t)(6 + s + sadj + 1) * n * 8 + 64 * 8;
+    return (size_t)(6 + s + sadj + 1 + (recompute ? 2 * sadj : 0)) * n * 8 + 64 * 8 + 64 * 8;
 }
 
 bool va_glv_stream_supported(int n, int stepper, int adaptive)
 {
     if (n < 1) return false;
-    if (va_glv_stream_smem(n, stepper) > 200 * 1024) return false; // vectors must fit shared memory (N up to ~1200)
+    if (va_glv_stream_smem(n, stepper, 1) > 200 * 1024) return false; // vectors must fit shared memory (N up to ~800)
     if (stepper == VA_RK_RK4) return !adaptive;
     if (stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5) return adaptive != 0;
     return false;
 }
 
-int va_glv_stream_block_doubles(int n, int stepper)
+int va_glv_stream_block_doubles(int n, int stepper, int recompute)
 {
     int sadj = 0;
     stages_of(stepper, &sadj);
-    return 8 + 2 * sadj * n;
+    return recompute ? 8 + n : 8 + 2 * sadj * n;
 }
 
 cudaError_t va_glv_stream_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;
-    const size_t smem = va_glv_stream_smem(a.n, a.stepper);
+    const size_t smem = va_glv_stream_smem(a.n, a.stepper, a.recompute);
     switch (a.stepper) {
     case VA_RK_RK4: return launch<TabRK4, false>(a, st, smem);
     case VA_RK_CK54: return launch<TabCK54, true>(a, st, smem);

@@ -1,0 +1,585 @@
+// va_glv_t8.cu -- GLV forward + discrete-adjoint kernel for 33..64 species, second generation of the headline path
+//                  (GLV N = 64, one million parameter sets): 64 threads per trajectory, 8x8 register tiles, three phases.
+//
+// f_i = x_i (r_i + (A x)_i), parameters [r, A row-major] (reference examples/GeneralizedLotkaVolterra/main.cpp:105-119).
+// Same algorithm as va_glv_wide.cu (reference lib/include/detail/runge_kutta.hpp:76-118 forward + odeint controlled
+// stepper; detail/backpropagation.hpp:83-158, 231-254 reverse); what changed is the thread <-> data map, chosen from
+// the ncu profile of the first generation (profiles/r01_glv64_ncu_full_ve.txt: FP64 pipe 48 % busy of which only 65 % were
+// the algorithmic DFMAs, 8 warps per SM, every stage a barrier -> loads -> DFMA -> exchange chain):
+//   * one CTA of 64 threads = one trajectory; the matrix is cut into 8x8 tiles of 8x8 entries (64 FP64 values = 128
+//     registers per thread). 8 loaded vector operands feed 64 DFMA (was 8 per 32), the partial sums are combined over
+//     8 lanes by select-free recursive halving (7 double shuffles), after which EVERY thread owns exactly one vector
+//     component: the stage recurrences are no longer computed redundantly (they were 2x redundant).
+//   * the gradient accumulator Abar (another 128 registers) cannot be live next to the matrix, so the reverse sweep is
+//     split: phase 2 propagates lambda through the stored steps with A^T in registers and writes the seeds
+//     v_m = w_m o X_m to the step block in the slab; phase 3 streams the blocks once more and accumulates
+//     Abar += v_m X_m^T -- 64 independent DFMA chains per thread, no reductions, no barriers inside a step: pure FP64
+//     throughput that fills the pipe while other CTAs of the SM sit in their latency-bound phases.
+//   * <= 255 registers per thread, 4 CTAs = 8 warps per SM. (The register file is partitioned per SM sub-partition, so
+//     warps per SM come in multiples of four: the next step, 12 warps, leaves 168 registers and spills the tile.)
+// Step blocks: [8-double header (t_n) | X_0..X_{s-1} | g_0..g_{s-1} | v_1..v_s] in a private slab per CTA (reused for
+// every trajectory -> L2 resident), streamed back by TMA bulk copies (cp.async.bulk + mbarrier), NB buffers deep. With a
+// single seed per trajectory the v section aliases the g section (g_m is dead once v_m exists).
+//
+// The accumulation order of every sum follows the reference (newest step first, stages s..1); matrix-vector products
+// use FMA and tree reductions, so values differ from the scalar reference by round-off (parity section).
+#include <cstdlib>
+
+#include "va_glv_common.cuh"
+
+#ifndef VA_T8_MINB
+#define VA_T8_MINB 4 // resident CTAs per SM the register allocation is sized for
+#endif
+#ifndef VA_T8_NB
+#define VA_T8_NB 3 // step-block buffers per CTA
+#endif
+
+namespace {
+
+constexpr int NP = 64;  // padded species count
+constexpr int NT = 64;  // threads per CTA = per trajectory
+constexpr int HDR = 8;  // doubles in a step-block header (hdr[0] = t_n)
+constexpr int NB = VA_T8_NB;
+
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// ---- mbarrier + TMA bulk copy (global -> shared) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "T8_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra T8_WAIT_DONE;\n"
+        "bra T8_WAIT_LOOP;\n"
+        "T8_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// max over the warp of non-negative doubles (or NaN, which orders above everything): two 32-bit redux operations on
+// the bit pattern instead of five double shuffles + DMNMX
+__device__ __forceinline__ double warp_max_nonneg(double e)
+{
+    const unsigned hi = (unsigned)__double2hiint(e), lo = (unsigned)__double2loint(e);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
+template <class Tab, bool ADAPTIVE, bool EXACT>
+__global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant__ VaGlvWideArgs a)
+{
+    constexpr int S = Tab::S, SADJ = Tab::SADJ;
+    constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
+    extern __shared__ __align__(128) double xg[]; // NB step-block buffers of a.blk_doubles
+    __shared__ __align__(16) double xs[2][NP];    // operand vector of the current matrix-vector product (double buffered)
+    __shared__ double red[2];
+    __shared__ __align__(8) uint64_t mbar[NB];
+
+    const int tid = threadIdx.x;
+    const int g = tid & 7;   // lane inside the 8-lane reduction group
+    const int hi = tid >> 3; // reduction group 0..7
+    const int own = tid;     // vector component this thread owns after a reduction (8 hi + g)
+    const int warp = tid >> 5;
+    const int n = a.n;
+    const int npar = n * n + n;
+    const int cap = a.cap;
+    const int blk = a.blk_doubles;
+    const int voff = blk - SADJ * NP;                        // v section of a step block
+    const uint32_t xg_bytes = (HDR + 2 * SADJ * NP) * 8;     // header, X and g
+    const bool vsep = voff != HDR + SADJ * NP;               // v has its own section (several seeds per trajectory)
+    double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
+    const double tf = a.tf;
+
+    // g-direction entries of a tile: FG(e) = 2g + (e&1) + 16 (e>>1): the 8 lanes of a group read their operands as four
+    // conflict-free LDS.128 (double2 index g + 8 j); FH is the same pattern along the group index (phase 3 rows)
+    auto FG = [&](int e) { return 2 * g + (e & 1) + 16 * (e >> 1); };
+    auto FH = [&](int e) { return 2 * hi + (e & 1) + 16 * (e >> 1); };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t mbar_parity = 0; // bit i: parity of the next completion of mbar[i]
+
+    // summed mode: this CTA's partial-sum row; every thread zeroes exactly the entries it later adds to
+    double *const part = a.partial + (int64_t)blockIdx.x * npar;
+    if (a.reduce == VA_REDUCE_SUM && a.n_out > 0) {
+        if (own < n) part[own] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int row = FH(k), col = FG(c);
+                if (row < n && col < n) part[n + row * n + col] = 0.0;
+            }
+    }
+    __syncthreads();
+
+    // y_own = sum_c M[k][c] xin[FG(c)] reduced over the group; M is held permuted (register row k <-> tile row k ^ g) so the
+    // recursive halving needs no selects. `after_sync` runs right behind the barrier, `extra` between the operand loads
+    // and the exchange rounds (work that does not depend on the result, off the critical path).
+    auto matvec = [&](const double(&M)[8][8], double X, int p, auto &&after_sync, auto &&extra) -> double {
+        xs[p][own] = X;
+        __syncthreads();
+        after_sync();
+        const double2 *xv = reinterpret_cast<const double2 *>(xs[p]) + g;
+        double s[8];
+        {
+            const double2 v = xv[0];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = M[k][0] * v.x;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = fma(M[k][1], v.y, s[k]);
+        }
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            const double2 v = xv[8 * j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = fma(M[k][2 * j], v.x, s[k]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = fma(M[k][2 * j + 1], v.y, s[k]);
+        }
+        extra();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += shx(s[4 + j], 4);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) s[j] += shx(s[2 + j], 2);
+        return s[0] + shx(s[1], 1);
+    };
+    auto nop = [] {};
+
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const double *pb = a.params + b * npar;
+        double M[8][8];
+        // ================================ phase 1: forward sweep =====================================
+        // tile rows 8 hi + (k ^ g), columns FG(c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int row = 8 * hi + (k ^ g);
+            if (EXACT) {
+                const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 2 * g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 v = __ldg(src + 8 * j);
+                    M[k][2 * j] = v.x;
+                    M[k][2 * j + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int col = FG(c);
+                    M[k][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                }
+            }
+        }
+        double r_own = 0.0, x = 0.0;
+        if (own < n) { r_own = __ldg(pb + own); x = __ldg(a.x0 + b * n + own); }
+
+        double t = a.ti, dt = a.dt0, K[S], g0;
+        int nck = 0, rejects = 0, status = 0, trials = 0;
+        bool fresh = true;
+        {
+            const double sum = matvec(M, x, 0, nop, nop);
+            g0 = r_own + sum;
+            K[0] = x * g0;
+        }
+        bool act = ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt);
+        double *sp = slab + HDR + own; // this thread's column in the current step block (advanced on acceptance)
+
+        while (act) {
+            if (fresh) {
+                if (nck >= cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
+                sp[0] = x;
+                sp[SADJ * NP] = g0;
+                if (tid == 0) sp[-HDR] = t; // own == 0: header of the current block
+                if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
+                trials = 0;
+                fresh = false;
+            }
+            // Stage m produces K_m = X_m (r + A X_m). The state of the NEXT stage (or the new solution after the last
+            // one), Y = x + dt sum_{j<=m} c_j K_j, is split so that only ONE DFMA follows the reduction:
+            //   Y = fma(c1, sum, base),  c1 = dt c_m X_m,  base = x + dt sum_{j<m} c_j K_j + c1 r   (all known early).
+            double X = fma(dt * a.coef.a[1][0], K[0], x);
+            double perr = 0.0; // sum_{j<SE-1} db_j K_j
+#pragma unroll
+            for (int m = 1; m < SE; ++m) {
+                const bool last = (m == SE - 1);
+                double c1 = 0.0, base = 0.0;
+                const double sum = matvec(M, X, m & 1, nop, [&] {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < m; ++j) {
+                        const double cz = last ? Tab::b(j) : Tab::a(m + 1, j);
+                        if (cz != 0.0) acc = fma(last ? a.coef.b[j] : a.coef.a[m + 1][j], K[j], acc);
+                    }
+                    const double cm = last ? Tab::b(m) : Tab::a(m + 1, m);
+                    c1 = (cm != 0.0) ? (dt * (last ? a.coef.b[m] : a.coef.a[m + 1][m])) * X : 0.0;
+                    base = fma(c1, r_own, fma(dt, acc, x));
+                    if (last && ADAPTIVE) {
+#pragma unroll
+                        for (int j = 0; j < m; ++j)
+                            if (Tab::db(j) != 0.0) perr = fma(a.coef.db[j], K[j], perr);
+                    }
+                });
+                const double Y = fma(c1, sum, base);
+                const double gg = r_own + sum;
+                K[m] = X * gg;
+                if (m < SADJ) { sp[m * NP] = X; sp[(SADJ + m) * NP] = gg; }
+                X = Y;
+            }
+            // X = new solution. f(xnew) is evaluated now: it is the FSAL stage of dopri5, and for the other steppers the
+            // first slope of the next step (speculative: discarded if the step is rejected).
+            const double gl = r_own + matvec(M, X, SE & 1, nop, nop);
+            const double Kl = X * gl;
+            if (Tab::FSAL) K[S - 1] = Kl;
+            double err = 0.0;
+            if (ADAPTIVE) {
+                double acc = perr;
+#pragma unroll
+                for (int j = SE - 1; j < S; ++j)
+                    if (Tab::db(j) != 0.0) acc = fma(a.coef.db[j], K[j], acc);
+                const double xerr = dt * acc;
+                // default_error_checker::error, max norm over species
+                double e = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
+                if (!(own < n)) e = 0.0;
+                e = warp_max_nonneg(e);
+                if ((tid & 31) == 0) red[warp] = e;
+                __syncthreads();
+                const long long e0 = __double_as_longlong(red[0]), e1 = __double_as_longlong(red[1]);
+                err = __longlong_as_double(e0 > e1 ? e0 : e1);
+            }
+            const bool accept = !ADAPTIVE || !(err > 1.0);
+            if (!accept) {
+                // default_step_adjuster::decrease_step
+                dt *= fmax(0.9 * inv_root<(Tab::ERROR_ORDER > 1 ? Tab::ERROR_ORDER - 1 : 1)>(err), 0.2);
+                ++rejects;
+                if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; }
+            } else {
+                x = X;
+                ++nck;
+                sp += blk;
+                if (ADAPTIVE) {
+                    t += dt;
+                    // default_step_adjuster::increase_step
+                    if (err < 0.5) {
+                        constexpr int P = Tab::STEPPER_ORDER;
+                        double floor_ = 1.0;
+#pragma unroll
+                        for (int k = 0; k < P; ++k) floor_ *= 0.2; // 5^-P
+                        // err <= 5^-P: the growth factor is exactly 0.9 * 5 (pow(5^-P, -1/P) == 5 in glibc as well)
+                        dt *= (err <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root<P>(err);
+                    }
+                    act = va_less_with_sign(t, tf, dt);
+                } else {
+                    t = a.ti + (double)nck * dt; // detail/runge_kutta.hpp:64
+                    act = va_less_eq_with_sign(t + dt, tf, dt);
+                }
+                fresh = true;
+                g0 = gl;
+                K[0] = Kl;
+            }
+        }
+        // close the trajectory: final time, status, x(tf)
+        const int T = nck;
+        if (tid == 0) sp[-HDR] = t; // header of block T carries the final time
+        if (own < n && !isfinite(x)) status |= VA_TRAJ_NONFINITE;
+        fence_proxy_async(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
+        status = __syncthreads_or(status);
+        const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
+        const double x_tf = x, t_final = t;
+        if (own < n) a.x_final[b * n + own] = failed ? nan("") : x;
+        if (tid == 0) {
+            if (a.n_accept) a.n_accept[b] = T;
+            if (a.n_reject) a.n_reject[b] = rejects;
+            if (a.status) a.status[b] = status;
+        }
+        if (a.n_out <= 0) continue;
+
+        // ================================ phase 2: adjoint of the state =====================================
+        for (int o = 0; o < a.n_out; ++o) {
+            double *lam_io = a.lambda + (b * a.n_out + o) * n;
+            double *mu_o = a.mu + (a.reduce == VA_REDUCE_SUM ? (int64_t)o : (b * a.n_out + o)) * npar;
+            if (failed) {
+                if (own < n) lam_io[own] = nan("");
+                if (a.reduce == VA_REDUCE_NONE)
+                    for (int k = tid; k < npar; k += NT) mu_o[k] = nan("");
+                continue;
+            }
+            // transposed tile: M[k][c] = A[FG(c)][8 hi + (k ^ g)]; the owned component stays `own`. A is re-read (L2 hit),
+            // once per seed: the tile must not stay live across phase 3, whose accumulator needs its registers.
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int row = FG(c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int col = 8 * hi + (k ^ g);
+                    if (EXACT) M[k][c] = __ldg(pb + NP + row * NP + col);
+                    else M[k][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                }
+            }
+            double lam;
+            if (a.objective == VA_OBJ_SUM) lam = (own < n) ? 1.0 : 0.0;
+            else if (a.objective == VA_OBJ_HALF_NORM2) lam = x_tf;
+            else lam = (own < n) ? lam_io[own] : 0.0;
+            double rbar = 0.0;
+
+            // stream the step blocks back, newest first: iteration it <-> step T-1-it, buffer it % NB, NB-1 blocks ahead
+            auto issue2 = [&](int it) {
+                if (it < T) {
+                    const int bi = it % NB;
+                    mbar_expect_tx(&mbar[bi], xg_bytes);
+                    bulk_g2s(xg + bi * blk, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi]);
+                }
+            };
+            __syncthreads(); // every thread is past its reads of the buffers (previous seed / trajectory)
+            if (tid == 0)
+                for (int it = 0; it < NB - 1; ++it) issue2(it);
+            double t_hi = t_final;
+            for (int it = 0; it < T; ++it) {
+                const int step = T - 1 - it, bi = it % NB;
+                mbar_wait(&mbar[bi], (mbar_parity >> bi) & 1);
+                mbar_parity ^= 1u << bi;
+                const double *bs = xg + bi * blk;
+                double *gv = slab + (int64_t)step * blk + voff + own; // v_1..v_s of this step, this thread's column
+                const double t_lo = bs[0];
+                const double dt_s = t_hi - t_lo; // StateStorage::GetDt: difference of the stored times
+                t_hi = t_lo;
+                double W[SADJ + 1];
+                W[0] = lam;
+#pragma unroll
+                for (int m = 1; m <= SADJ; ++m) W[m] = Tab::b(m - 1) != 0.0 ? (a.coef.b[m - 1] * dt_s) * lam : 0.0;
+                // v = w_m o X_{m-1} for the stage about to be processed; later stages get it from the previous one
+                double v = W[SADJ] * bs[HDR + (SADJ - 1) * NP + own];
+#pragma unroll
+                for (int m = SADJ; m >= 1; --m) {
+                    gv[(m - 1) * NP] = v;
+                    double wg = 0.0, c1 = 0.0, c2 = 0.0;
+                    const double sum = matvec(
+                        M, v, m & 1,
+                        [&] {
+                            // every thread is past its reads of the previous iteration's buffer: refill it
+                            if (m == SADJ && tid == 0) issue2(it + NB - 1);
+                        },
+                        [&] {
+                            // gx = (A^T v)_own + w_m g_{m-1}. The next stage's v = (w_{m-1} + gx a dt) X_{m-2} is arranged
+                            // as fma(sum, c1, c2) with c1, c2 known before the reduction returns
+                            wg = W[m] * bs[HDR + (SADJ + m - 1) * NP + own];
+                            if (m > 1) {
+                                const double Xn = bs[HDR + (m - 2) * NP + own];
+                                if (Tab::a(m - 1, m - 2) != 0.0) c1 = (a.coef.a[m - 1][m - 2] * dt_s) * Xn;
+                                c2 = fma(wg, c1, W[m - 1] * Xn);
+                            }
+                        });
+                    const double v_next = fma(sum, c1, c2);
+                    const double gx = sum + wg;
+                    const double gxd = gx * dt_s;
+                    rbar += v;
+                    W[0] += gx;
+#pragma unroll
+                    for (int k = 1; k < m; ++k)
+                        if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gxd, a.coef.a[m - 1][k - 1], W[k]);
+                    v = v_next;
+                }
+                lam = W[0];
+            }
+            if (own < n) lam_io[own] = lam;
+
+            // ================================ phase 3: gradient accumulation =====================================
+            // Abar[i][j] += v_m[i] X_{m-1}[j] over all steps and stages; accumulator tile rows FH(k), columns FG(c)
+            fence_proxy_async(); // the v sections were written through the generic proxy
+            __syncthreads();
+            auto issue3 = [&](int it) {
+                if (it < T) {
+                    const int bi = it % NB;
+                    const double *src = slab + (int64_t)(T - 1 - it) * blk;
+                    if (vsep) {
+                        mbar_expect_tx(&mbar[bi], (HDR + 2 * SADJ * NP) * 8);
+                        bulk_g2s(xg + bi * blk, src, (HDR + SADJ * NP) * 8, &mbar[bi]);
+                        bulk_g2s(xg + bi * blk + voff, src + voff, SADJ * NP * 8, &mbar[bi]);
+                    } else {
+                        mbar_expect_tx(&mbar[bi], xg_bytes);
+                        bulk_g2s(xg + bi * blk, src, xg_bytes, &mbar[bi]);
+                    }
+                }
+            };
+            if (tid == 0)
+                for (int it = 0; it < NB - 1; ++it) issue3(it);
+            double Ab[8][8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) Ab[k][c] = 0.0;
+            for (int it = 0; it < T; ++it) {
+                const int bi = it % NB;
+                __syncthreads(); // every thread is done with iteration it-1: its buffer can be refilled
+                if (tid == 0) issue3(it + NB - 1);
+                mbar_wait(&mbar[bi], (mbar_parity >> bi) & 1);
+                mbar_parity ^= 1u << bi;
+                const double *bs = xg + bi * blk;
+#pragma unroll
+                for (int m = SADJ; m >= 1; --m) {
+                    const double2 *vv = reinterpret_cast<const double2 *>(bs + voff + (m - 1) * NP) + hi;
+                    const double2 *xx = reinterpret_cast<const double2 *>(bs + HDR + (m - 1) * NP) + g;
+                    double vr[8], xc[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 p = vv[8 * j], q = xx[8 * j];
+                        vr[2 * j] = p.x; vr[2 * j + 1] = p.y;
+                        xc[2 * j] = q.x; xc[2 * j + 1] = q.y;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) Ab[k][c] = fma(vr[k], xc[c], Ab[k][c]);
+                }
+            }
+            if (a.reduce == VA_REDUCE_NONE) {
+                if (own < n) mu_o[own] = rbar;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int row = FH(k);
+                    if (EXACT) {
+                        double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP + 2 * g);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[8 * j] = make_double2(Ab[k][2 * j], Ab[k][2 * j + 1]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int col = FG(c);
+                            if (row < n && col < n) mu_o[n + row * n + col] = Ab[k][c];
+                        }
+                    }
+                }
+            } else {
+                // summed objective: fire-and-forget FP64 reductions into this CTA's private partial-sum row (one writer
+                // per address, program order -> deterministic)
+                if (own < n) atomicAdd(part + own, rbar);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int row = FH(k), col = FG(c);
+                        if (row < n && col < n) atomicAdd(part + n + row * n + col, Ab[k][c]);
+                    }
+            }
+        }
+        __syncthreads(); // slab and shared buffers are reused by the next trajectory
+    }
+}
+
+template <class Tab, bool ADAPTIVE, bool EXACT>
+cudaError_t launch_k(const VaGlvWideArgs &a, cudaStream_t st)
+{
+    const size_t smem = (size_t)NB * a.blk_doubles * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_glv_t8<Tab, ADAPTIVE, EXACT><<<a.grid, NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <class Tab, bool ADAPTIVE>
+cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
+{
+    VaGlvWideArgs a = a_in;
+    // tableau values travel in the kernel arguments (constant bank): DFMA takes them as c[bank][offset] operands,
+    // while the compile-time copy in Tab:: only decides which terms exist
+    for (int m = 0; m < Tab::S; ++m) {
+        for (int j = 0; j < m && j < 6; ++j) a.coef.a[m][j] = Tab::a(m, j);
+        a.coef.b[m] = Tab::b(m);
+        a.coef.db[m] = Tab::db(m);
+    }
+    return a.n == NP ? launch_k<Tab, ADAPTIVE, true>(a, st) : launch_k<Tab, ADAPTIVE, false>(a, st);
+}
+
+template <class Tab, bool ADAPTIVE>
+cudaError_t occupancy(int n, size_t smem, int *ctas_per_sm)
+{
+    if (n == NP) {
+        cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_t8<Tab, ADAPTIVE, true>, NT, smem);
+    }
+    cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_t8<Tab, ADAPTIVE, false>, NT, smem);
+}
+
+int sadj_of(int stepper)
+{
+    switch (stepper) {
+    case VA_RK_RK4: return TabRK4::SADJ;
+    case VA_RK_CK54: return TabCK54::SADJ;
+    case VA_RK_DOPRI5: return TabDOPRI5::SADJ;
+    }
+    return 0;
+}
+
+} // namespace
+
+bool va_glv_t8_supported(int n, int stepper, int adaptive)
+{
+    if (n <= 32 || n > NP) return false; // smaller systems: va_glv_wide.cu (warp per trajectory)
+    if (stepper == VA_RK_RK4) return !adaptive;
+    if (stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5) return adaptive != 0;
+    return false;
+}
+
+// step block: [8-double header | X_0..X_{s-1} | g_0..g_{s-1} | v_1..v_s]; with one seed per trajectory v aliases g
+int va_glv_t8_block_doubles(int stepper, int n_out) { return HDR + (n_out > 1 ? 3 : 2) * sadj_of(stepper) * NP; }
+
+cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads)
+{
+    int sms = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess) return err;
+    const size_t smem = (size_t)NB * va_glv_t8_block_doubles(stepper, n_out) * 8;
+    int occ = 0;
+    switch (stepper) {
+    case VA_RK_RK4: err = occupancy<TabRK4, false>(n, smem, &occ); break;
+    case VA_RK_CK54: err = occupancy<TabCK54, true>(n, smem, &occ); break;
+    case VA_RK_DOPRI5: err = occupancy<TabDOPRI5, true>(n, smem, &occ); break;
+    default: return cudaErrorInvalidValue;
+    }
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    if (const char *env = getenv("VA_GLV_CTAS_PER_SM")) { // experiment knob: fewer resident CTAs than the occupancy limit
+        const int v = atoi(env);
+        if (v >= 1 && v < occ) occ = v;
+    }
+    *ctas_per_sm = occ;
+    *grid = sms * occ;
+    *threads = NT;
+    return cudaSuccess;
+}
+
+cudaError_t va_glv_t8_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
+{
+    if (a.B <= 0) return cudaSuccess;
+    switch (a.stepper) {
+    case VA_RK_RK4: return launch<TabRK4, false>(a, st);
+    case VA_RK_CK54: return launch<TabCK54, true>(a, st);
+    case VA_RK_DOPRI5: return launch<TabDOPRI5, true>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
