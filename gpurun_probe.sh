@@ -1,11 +1,3 @@
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1_final.json 2>gpurun_out/bench_r1_final.err
-for w in glv16 vdp harmonic glv256; do python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/bench_r1_$w.json 2>>gpurun_out/bench_r1_final.err; done
-python bench.py --reduce none --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_r1_glv64_reduce_none.json 2>>gpurun_out/bench_r1_final.err
-python -c "
-import json,glob
-for f in sorted(glob.glob('gpurun_out/bench_r1_*.json')):
-    try:
-        d=json.load(open(f)); print(f, round(d['value']), round(d['ms_per_step'],2), d.get('roofline',{}).get('frac'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('value'))
-    except Exception as e: print(f, 'ERR', e)
-"
-tail -3 gpurun_out/bench_r1_final.err
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1_t8.json 2>gpurun_out/bench_r1_t8.err; cut -c1-250 gpurun_out/bench_r1_t8.json
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_glv_t8 -s 2 -c 1 -f -o gpurun_out/prof_t8_c python bench.py --batch 16384 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | cut -c1-100

@@ -39,7 +39,7 @@ cudaError_t va_glv_wide_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
 // second-generation register kernel for 33..64 species (va_glv_t8.cu): 64 threads per trajectory, 8x8 tiles, three phases
 bool va_glv_t8_supported(int n, int stepper, int adaptive);
 int va_glv_t8_block_doubles(int stepper, int n_out);
-cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads);
+cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);
 cudaError_t va_glv_t8_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
 // streamed-matrix GLV family (va_glv_stream.cu): any N, one 256-thread CTA per trajectory, same argument block

@@ -476,8 +476,8 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         e->t8 = va_glv_t8_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_V1");
         cudaError_t ce;
         if (e->t8) {
-            ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads);
-            e->tpc = e->pair = 1;
+            ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
+            e->pair = 1;
             e->glv_blk = va_glv_t8_block_doubles(desc->stepper, desc->n_out);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
         } else {

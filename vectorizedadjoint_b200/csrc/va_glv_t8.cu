@@ -30,6 +30,9 @@
 #ifndef VA_T8_MINB
 #define VA_T8_MINB 4 // resident CTAs per SM the register allocation is sized for
 #endif
+#ifndef VA_T8_SLOTS
+#define VA_T8_SLOTS 4 // trajectories ("slots") per CTA: 4 -> one 256-thread CTA per SM; 1 -> 64-thread CTAs, VA_T8_MINB per SM
+#endif
 #ifndef VA_T8_NB
 #define VA_T8_NB 3 // step-block buffers per CTA
 #endif
@@ -37,7 +40,11 @@
 namespace {
 
 constexpr int NP = 64;  // padded species count
-constexpr int NT = 64;  // threads per CTA = per trajectory
+constexpr int NTT = 64; // threads per trajectory
+constexpr int SLOTS = VA_T8_SLOTS;
+constexpr int NT = NTT * SLOTS; // threads per CTA
+constexpr int MINB = SLOTS == 1 ? VA_T8_MINB : 1;
+
 constexpr int HDR = 8;  // doubles in a step-block header (hdr[0] = t_n)
 constexpr int NB = VA_T8_NB;
 
@@ -85,21 +92,47 @@ __device__ __forceinline__ double warp_max_nonneg(double e)
     return __hiloint2double((int)mh, (int)ml);
 }
 
+// e^(-1/P), the controller's step-size root (odeint default_step_adjuster; pow() in the reference). Every thread evaluates
+// it on the critical path between two steps, so the dependent chain is kept short: float seed (relative error ~1e-6), two
+// Newton steps on y^-P = e (error -> ~3e-12 -> below one ulp), y^P by squaring. e is clamped so that e y^P cannot overflow.
+template <int P>
+__device__ __forceinline__ double inv_root_short(double e)
+{
+    e = fmin(e, 1e30);
+    double y = (double)__powf((float)e, -1.0f / (float)P);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y;
+        const double yp = P == 1 ? y : P == 2 ? y2 : P == 3 ? y2 * y : P == 4 ? y2 * y2 : P == 5 ? (y2 * y2) * y : (y2 * y2) * y2;
+        static_assert(P >= 1 && P <= 6, "unsupported order");
+        y = fma(y * (1.0 / P), fma(-e, yp, 1.0), y);
+    }
+    return y;
+}
+
 template <class Tab, bool ADAPTIVE, bool EXACT>
-__global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant__ VaGlvWideArgs a)
+__global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
-    extern __shared__ __align__(128) double xg[]; // NB step-block buffers of a.blk_doubles
-    __shared__ __align__(16) double xs[2][NP];    // operand vector of the current matrix-vector product (double buffered)
-    __shared__ double red[2];
-    __shared__ __align__(8) uint64_t mbar[NB];
+    extern __shared__ __align__(128) double xg_all[]; // per slot: NB step-block buffers of a.blk_doubles
+    __shared__ __align__(16) double xs_all[SLOTS][2][NP]; // operand vector of the current matrix-vector product (double buffered)
+    __shared__ double red_all[SLOTS][2];
+    __shared__ int st_all[SLOTS][2];
+    __shared__ __align__(8) uint64_t mbar_all[SLOTS][NB];
 
-    const int tid = threadIdx.x;
+    // Warp w of the CTA runs on SM sub-partition w % 4 (tools/microbench/smsp_map.cu). Slot s takes the warp pair
+    // {2 s, 2 s + 1}: the two warps of a trajectory sit on different sub-partitions, and every sub-partition hosts one warp of
+    // two different trajectories. (Tried and dropped: a shared-memory lock that makes those two warps take turns on the FP64
+    // pipe -- a burst is shorter than the latency chain behind it, so serialising bursts only adds the lock's latency:
+    // 4.82 M vs 5.71 M gradients/s.)
+    const int wc = threadIdx.x >> 5;
+    const int slot = SLOTS == 1 ? 0 : ((wc >> 2) << 1) | ((wc >> 1) & 1);
+    const int warp = wc & 1;                       // warp inside the trajectory
+    const int tid = warp * 32 + (threadIdx.x & 31); // thread inside the trajectory
     const int g = tid & 7;   // lane inside the 8-lane reduction group
     const int hi = tid >> 3; // reduction group 0..7
     const int own = tid;     // vector component this thread owns after a reduction (8 hi + g)
-    const int warp = tid >> 5;
     const int n = a.n;
     const int npar = n * n + n;
     const int cap = a.cap;
@@ -107,12 +140,31 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
     const int voff = blk - SADJ * NP;                        // v section of a step block
     const uint32_t xg_bytes = (HDR + 2 * SADJ * NP) * 8;     // header, X and g
     const bool vsep = voff != HDR + SADJ * NP;               // v has its own section (several seeds per trajectory)
-    double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
+    const int64_t gslot = (int64_t)blockIdx.x * SLOTS + slot; // global slot: owns one slab and one partial-sum row
+    double *const slab = a.slab + gslot * a.slab_stride;
+    double *const xg = xg_all + (size_t)slot * NB * blk;
+    double(*xs)[NP] = xs_all[slot];
+    double *red = red_all[slot];
+    uint64_t *mbar = mbar_all[slot];
     const double tf = a.tf;
 
-    // g-direction entries of a tile: FG(e) = 2g + (e&1) + 16 (e>>1): the 8 lanes of a group read their operands as four
-    // conflict-free LDS.128 (double2 index g + 8 j); FH is the same pattern along the group index (phase 3 rows)
-    auto FG = [&](int e) { return 2 * g + (e & 1) + 16 * (e >> 1); };
+    // barrier over the 64 threads of one trajectory
+    auto slot_sync = [&]() {
+        if (SLOTS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
+    };
+    auto slot_or = [&](int v) -> int {
+        v = __reduce_or_sync(0xffffffffu, v);
+        if ((tid & 31) == 0) st_all[slot][warp] = v;
+        slot_sync();
+        return st_all[slot][0] | st_all[slot][1];
+    };
+
+    // g-direction entries of a tile, as double2 offsets PO(j), j = 0..3: the 8 lanes of a group read 8 consecutive double2
+    // (one conflict-free LDS.128, broadcast to the 4 groups of the warp). FG(e) = 2 PO(e>>1) + (e&1); FH is the same
+    // pattern along the group index (phase 3 rows).
+    auto PO = [&](int j) { return g + 8 * j; };
+    auto FG = [&](int e) { return 2 * PO(e >> 1) + (e & 1); };
     auto FH = [&](int e) { return 2 * hi + (e & 1) + 16 * (e >> 1); };
 
     if (tid == 0) {
@@ -122,8 +174,8 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
     }
     uint32_t mbar_parity = 0; // bit i: parity of the next completion of mbar[i]
 
-    // summed mode: this CTA's partial-sum row; every thread zeroes exactly the entries it later adds to
-    double *const part = a.partial + (int64_t)blockIdx.x * npar;
+    // summed mode: this slot's partial-sum row; every thread zeroes exactly the entries it later adds to
+    double *const part = a.partial + gslot * npar;
     if (a.reduce == VA_REDUCE_SUM && a.n_out > 0) {
         if (own < n) part[own] = 0.0;
 #pragma unroll
@@ -136,17 +188,19 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
     }
     __syncthreads();
 
-    // y_own = sum_c M[k][c] xin[FG(c)] reduced over the group; M is held permuted (register row k <-> tile row k ^ g) so the
-    // recursive halving needs no selects. `after_sync` runs right behind the barrier, `extra` between the operand loads
-    // and the exchange rounds (work that does not depend on the result, off the critical path).
+    // y_own = sum_c M[k][c] xin[FG(c)] summed over the group; M is held permuted (register row k <-> tile row k ^ g): lane
+    // g ^ j keeps the partial sum of lane g's row in register j, so the group sum is ONE round of 7 independent double
+    // shuffles and an add tree (recursive halving needs as many shuffles in three dependent rounds: measured 2.5 % slower).
+    // `after_sync` runs right behind the barrier, `extra` between the DFMAs and the exchange (work that does not depend on
+    // the result, off the critical path).
     auto matvec = [&](const double(&M)[8][8], double X, int p, auto &&after_sync, auto &&extra) -> double {
         xs[p][own] = X;
-        __syncthreads();
+        slot_sync();
         after_sync();
-        const double2 *xv = reinterpret_cast<const double2 *>(xs[p]) + g;
+        const double2 *xv = reinterpret_cast<const double2 *>(xs[p]);
         double s[8];
         {
-            const double2 v = xv[0];
+            const double2 v = xv[PO(0)];
 #pragma unroll
             for (int k = 0; k < 8; ++k) s[k] = M[k][0] * v.x;
 #pragma unroll
@@ -154,22 +208,22 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
         }
 #pragma unroll
         for (int j = 1; j < 4; ++j) {
-            const double2 v = xv[8 * j];
+            const double2 v = xv[PO(j)];
 #pragma unroll
             for (int k = 0; k < 8; ++k) s[k] = fma(M[k][2 * j], v.x, s[k]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) s[k] = fma(M[k][2 * j + 1], v.y, s[k]);
         }
         extra();
+        double t[8];
+        t[0] = s[0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] += shx(s[4 + j], 4);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) s[j] += shx(s[2 + j], 2);
-        return s[0] + shx(s[1], 1);
+        for (int j = 1; j < 8; ++j) t[j] = shx(s[j], j);
+        return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
     };
     auto nop = [] {};
 
-    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+    for (int64_t b = gslot; b < a.B; b += (int64_t)gridDim.x * SLOTS) {
         const double *pb = a.params + b * npar;
         double M[8][8];
         // ================================ phase 1: forward sweep =====================================
@@ -178,10 +232,10 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
         for (int k = 0; k < 8; ++k) {
             const int row = 8 * hi + (k ^ g);
             if (EXACT) {
-                const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP + 2 * g);
+                const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double2 v = __ldg(src + 8 * j);
+                    const double2 v = __ldg(src + PO(j));
                     M[k][2 * j] = v.x;
                     M[k][2 * j + 1] = v.y;
                 }
@@ -250,29 +304,37 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
             }
             // X = new solution. f(xnew) is evaluated now: it is the FSAL stage of dopri5, and for the other steppers the
             // first slope of the next step (speculative: discarded if the step is rejected).
-            const double gl = r_own + matvec(M, X, SE & 1, nop, nop);
-            const double Kl = X * gl;
-            if (Tab::FSAL) K[S - 1] = Kl;
-            double err = 0.0;
-            if (ADAPTIVE) {
+            // default_error_checker::error, max norm over species: each warp's maximum crosses to the other warp together
+            // with the operands of this product (no barrier of its own) unless the error needs the FSAL slope.
+            constexpr bool ERR_EARLY = ADAPTIVE && !(Tab::FSAL && Tab::db(S - 1) != 0.0);
+            auto err_local = [&]() {
                 double acc = perr;
 #pragma unroll
                 for (int j = SE - 1; j < S; ++j)
                     if (Tab::db(j) != 0.0) acc = fma(a.coef.db[j], K[j], acc);
                 const double xerr = dt * acc;
-                // default_error_checker::error, max norm over species
                 double e = fabs(xerr) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
                 if (!(own < n)) e = 0.0;
                 e = warp_max_nonneg(e);
                 if ((tid & 31) == 0) red[warp] = e;
-                __syncthreads();
+            };
+            if (ERR_EARLY) err_local();
+            const double gl = r_own + matvec(M, X, SE & 1, nop, nop);
+            const double Kl = X * gl;
+            if (Tab::FSAL) K[S - 1] = Kl;
+            double err = 0.0;
+            if (ADAPTIVE) {
+                if (!ERR_EARLY) {
+                    err_local();
+                    slot_sync();
+                }
                 const long long e0 = __double_as_longlong(red[0]), e1 = __double_as_longlong(red[1]);
                 err = __longlong_as_double(e0 > e1 ? e0 : e1);
             }
             const bool accept = !ADAPTIVE || !(err > 1.0);
             if (!accept) {
                 // default_step_adjuster::decrease_step
-                dt *= fmax(0.9 * inv_root<(Tab::ERROR_ORDER > 1 ? Tab::ERROR_ORDER - 1 : 1)>(err), 0.2);
+                dt *= fmax(0.9 * inv_root_short<(Tab::ERROR_ORDER > 1 ? Tab::ERROR_ORDER - 1 : 1)>(err), 0.2);
                 ++rejects;
                 if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; }
             } else {
@@ -288,7 +350,7 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
 #pragma unroll
                         for (int k = 0; k < P; ++k) floor_ *= 0.2; // 5^-P
                         // err <= 5^-P: the growth factor is exactly 0.9 * 5 (pow(5^-P, -1/P) == 5 in glibc as well)
-                        dt *= (err <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root<P>(err);
+                        dt *= (err <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root_short<P>(err);
                     }
                     act = va_less_with_sign(t, tf, dt);
                 } else {
@@ -305,7 +367,7 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
         if (tid == 0) sp[-HDR] = t; // header of block T carries the final time
         if (own < n && !isfinite(x)) status |= VA_TRAJ_NONFINITE;
         fence_proxy_async(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
-        status = __syncthreads_or(status);
+        status = slot_or(status);
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
         const double x_tf = x, t_final = t;
         if (own < n) a.x_final[b * n + own] = failed ? nan("") : x;
@@ -323,7 +385,7 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
             if (failed) {
                 if (own < n) lam_io[own] = nan("");
                 if (a.reduce == VA_REDUCE_NONE)
-                    for (int k = tid; k < npar; k += NT) mu_o[k] = nan("");
+                    for (int k = tid; k < npar; k += NTT) mu_o[k] = nan("");
                 continue;
             }
             // transposed tile: M[k][c] = A[FG(c)][8 hi + (k ^ g)]; the owned component stays `own`. A is re-read (L2 hit),
@@ -352,7 +414,7 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
                     bulk_g2s(xg + bi * blk, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi]);
                 }
             };
-            __syncthreads(); // every thread is past its reads of the buffers (previous seed / trajectory)
+            slot_sync(); // every thread is past its reads of the buffers (previous seed / trajectory)
             if (tid == 0)
                 for (int it = 0; it < NB - 1; ++it) issue2(it);
             double t_hi = t_final;
@@ -408,7 +470,7 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
             // ================================ phase 3: gradient accumulation =====================================
             // Abar[i][j] += v_m[i] X_{m-1}[j] over all steps and stages; accumulator tile rows FH(k), columns FG(c)
             fence_proxy_async(); // the v sections were written through the generic proxy
-            __syncthreads();
+            slot_sync();
             auto issue3 = [&](int it) {
                 if (it < T) {
                     const int bi = it % NB;
@@ -432,7 +494,7 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
                 for (int c = 0; c < 8; ++c) Ab[k][c] = 0.0;
             for (int it = 0; it < T; ++it) {
                 const int bi = it % NB;
-                __syncthreads(); // every thread is done with iteration it-1: its buffer can be refilled
+                slot_sync(); // every thread is done with iteration it-1: its buffer can be refilled
                 if (tid == 0) issue3(it + NB - 1);
                 mbar_wait(&mbar[bi], (mbar_parity >> bi) & 1);
                 mbar_parity ^= 1u << bi;
@@ -440,11 +502,11 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
                     const double2 *vv = reinterpret_cast<const double2 *>(bs + voff + (m - 1) * NP) + hi;
-                    const double2 *xx = reinterpret_cast<const double2 *>(bs + HDR + (m - 1) * NP) + g;
+                    const double2 *xx = reinterpret_cast<const double2 *>(bs + HDR + (m - 1) * NP);
                     double vr[8], xc[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const double2 p = vv[8 * j], q = xx[8 * j];
+                        const double2 p = vv[8 * j], q = xx[PO(j)];
                         vr[2 * j] = p.x; vr[2 * j + 1] = p.y;
                         xc[2 * j] = q.x; xc[2 * j + 1] = q.y;
                     }
@@ -460,9 +522,9 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
                 for (int k = 0; k < 8; ++k) {
                     const int row = FH(k);
                     if (EXACT) {
-                        double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP + 2 * g);
+                        double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[8 * j] = make_double2(Ab[k][2 * j], Ab[k][2 * j + 1]);
+                        for (int j = 0; j < 4; ++j) dst[PO(j)] = make_double2(Ab[k][2 * j], Ab[k][2 * j + 1]);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -484,14 +546,14 @@ __global__ void __launch_bounds__(NT, VA_T8_MINB) k_glv_t8(const __grid_constant
                     }
             }
         }
-        __syncthreads(); // slab and shared buffers are reused by the next trajectory
+        slot_sync(); // slab and shared buffers are reused by the next trajectory
     }
 }
 
 template <class Tab, bool ADAPTIVE, bool EXACT>
 cudaError_t launch_k(const VaGlvWideArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)NB * a.blk_doubles * 8;
+    const size_t smem = (size_t)SLOTS * NB * a.blk_doubles * 8;
     cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_glv_t8<Tab, ADAPTIVE, EXACT><<<a.grid, NT, smem, st>>>(a);
@@ -548,12 +610,12 @@ bool va_glv_t8_supported(int n, int stepper, int adaptive)
 // step block: [8-double header | X_0..X_{s-1} | g_0..g_{s-1} | v_1..v_s]; with one seed per trajectory v aliases g
 int va_glv_t8_block_doubles(int stepper, int n_out) { return HDR + (n_out > 1 ? 3 : 2) * sadj_of(stepper) * NP; }
 
-cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads)
+cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta)
 {
     int sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess) return err;
-    const size_t smem = (size_t)NB * va_glv_t8_block_doubles(stepper, n_out) * 8;
+    const size_t smem = (size_t)SLOTS * NB * va_glv_t8_block_doubles(stepper, n_out) * 8;
     int occ = 0;
     switch (stepper) {
     case VA_RK_RK4: err = occupancy<TabRK4, false>(n, smem, &occ); break;
@@ -570,6 +632,7 @@ cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *gri
     *ctas_per_sm = occ;
     *grid = sms * occ;
     *threads = NT;
+    *slots_per_cta = SLOTS;
     return cudaSuccess;
 }
 
