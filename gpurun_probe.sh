@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1_t8.json 2>gpurun_out/bench_r1_t8.err; cut -c1-250 gpurun_out/bench_r1_t8.json
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_glv_t8 -s 2 -c 1 -f -o gpurun_out/prof_t8_c python bench.py --batch 16384 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | cut -c1-100
+timeout 600 python -m pytest tests -m gpu -x -q -k glv 2>&1 | tail -3
+timeout 200 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'])"

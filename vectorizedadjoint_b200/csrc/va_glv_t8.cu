@@ -123,9 +123,10 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 
     // Warp w of the CTA runs on SM sub-partition w % 4 (tools/microbench/smsp_map.cu). Slot s takes the warp pair
     // {2 s, 2 s + 1}: the two warps of a trajectory sit on different sub-partitions, and every sub-partition hosts one warp of
-    // two different trajectories. (Tried and dropped: a shared-memory lock that makes those two warps take turns on the FP64
-    // pipe -- a burst is shorter than the latency chain behind it, so serialising bursts only adds the lock's latency:
-    // 4.82 M vs 5.71 M gradients/s.)
+    // two different trajectories. (Tried and dropped, three times: making those two warps take turns on the FP64 pipe --
+    // with an atomic lock, with advisory flags, and with flags whose stores and loads are data-dependent on the burst so
+    // that ptxas cannot move them: 4.82 M, 4.60 M and 4.53 M gradients/s against 5.7 M without. ncu shows bursts stretched
+    // from ~155 to ~280 cycles by the neighbour, but serialising them costs more than the overlap.)
     const int wc = threadIdx.x >> 5;
     const int slot = SLOTS == 1 ? 0 : ((wc >> 2) << 1) | ((wc >> 1) & 1);
     const int warp = wc & 1;                       // warp inside the trajectory
