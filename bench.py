@@ -140,9 +140,9 @@ def reference_arm(args):
 
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per full-size launch, from the committed
-    ncu --set full capture (profiles/r01_traffic.json); None when no capture has been recorded."""
+    ncu --set full capture (profiles/r01_traffic_t8.json); None when no capture has been recorded."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic_t8.json")) as f:
             d = json.load(f)
         return d.get("dram_bytes_per_launch"), d.get("launch_parameter_sets", 1 << 20)
     except Exception:
@@ -313,6 +313,7 @@ def main():
     n_rej = torch.empty(Bl, dtype=torch.int32, device=dev)
     status = torch.empty(Bl, dtype=torch.int32, device=dev)
     eng = va.Engine(va.SYS_GLV, N, va.RK_CK54, True, TOL, TOL, device=local)
+    info = eng.info()
     side = torch.cuda.Stream(device=dev)  # a real (non-default) stream: kernels, events and NCCL ordering all live on it
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
@@ -379,14 +380,15 @@ def main():
             "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
             "traffic": (lambda tb: int(tb[0] * Bl / tb[1]) if tb[0] else None)(_ncu_traffic()),
             "peak_source": "DFMA microbenchmark run live on this GPU (va_measure_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
-            "kernel": "k_glv_wide<TabCK54,adaptive,N=64> (one launch per step per GPU; + a 296-row reduction kernel)",
+            "kernel": "k_glv_t8<TabCK54,adaptive,exact> (va_glv_t8.cu; one launch per step per GPU, %d CTAs x %d threads, 64 threads per "
+                      "trajectory; + one row-reduction kernel over the per-slot partial sums)" % (info["sm_count"] * info["ctas_per_sm"], info["threads_per_cta"]),
             "kernel_ms": kernel_ms, "flops_per_launch": flops_exec, "flops_counting": "executed algorithmic FP64 flops of rank 0: "
             "(6T+5R)(2N^2+2N) forward + 6T(4N^2+3N) reverse, store-stages policy (no stage recompute)",
             "achieved_reference_policy_formula": flops_refpolicy / (kernel_ms * 1e-3) / 1e12,
             "mean_accepted_steps": T_sum / max(Bl, 1), "mean_rejected": R_sum / max(Bl, 1), "failed_trajectories": bad,
             "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_meas,
                     "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_meas) if hbm_meas else None,
-                    "note": "compulsory bytes only (parameters in, x(tf), dJ/dx0 out); checkpoints stay in L2"},
+                    "note": "compulsory bytes only (parameters in, x(tf), dJ/dx0 out); measured DRAM traffic incl. checkpoint blocks spilled from L2 is roofline.traffic"},
         }
         line["clocks"] = clk
 

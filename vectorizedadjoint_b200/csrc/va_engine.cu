@@ -479,6 +479,11 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
             ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
             e->pair = 1;
             e->glv_blk = va_glv_t8_block_doubles(desc->stepper, desc->n_out);
+            // the kernel marks its checkpoint slabs evict_last: give that class the largest L2 share the device allows
+            int max_persist = 0;
+            if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device) == cudaSuccess && max_persist > 0)
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            if (getenv("VA_DEBUG")) fprintf(stderr, "va: persisting L2 limit %d bytes\n", max_persist);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
         } else {
             ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);

@@ -60,11 +60,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
+}
+// L2 residency control. The slabs (592 x ~130 KB of step blocks in flight per GPU) are written, read twice and then
+// overwritten; the parameters (35 GB per pass) stream through once. Without hints the stream evicts the slabs (ncu:
+// 280 KB of DRAM traffic per trajectory against 35 KB of compulsory bytes), so slab accesses carry evict_last and the
+// last read of the parameters evict_first.
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(double *p, double v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy));
+}
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy)
+{
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -148,6 +175,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     double *red = red_all[slot];
     uint64_t *mbar = mbar_all[slot];
     const double tf = a.tf;
+    const uint64_t keep = policy_evict_last();
 
     // barrier over the 64 threads of one trajectory
     auto slot_sync = [&]() {
@@ -265,9 +293,9 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         while (act) {
             if (fresh) {
                 if (nck >= cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
-                sp[0] = x;
-                sp[SADJ * NP] = g0;
-                if (tid == 0) sp[-HDR] = t; // own == 0: header of the current block
+                st_hint(sp, x, keep);
+                st_hint(sp + SADJ * NP, g0, keep);
+                if (tid == 0) st_hint(sp - HDR, t, keep); // own == 0: header of the current block
                 if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
                 trials = 0;
                 fresh = false;
@@ -300,7 +328,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 const double Y = fma(c1, sum, base);
                 const double gg = r_own + sum;
                 K[m] = X * gg;
-                if (m < SADJ) { sp[m * NP] = X; sp[(SADJ + m) * NP] = gg; }
+                if (m < SADJ) { st_hint(sp + m * NP, X, keep); st_hint(sp + (SADJ + m) * NP, gg, keep); }
                 X = Y;
             }
             // X = new solution. f(xnew) is evaluated now: it is the FSAL stage of dopri5, and for the other steppers the
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         }
         // close the trajectory: final time, status, x(tf)
         const int T = nck;
-        if (tid == 0) sp[-HDR] = t; // header of block T carries the final time
+        if (tid == 0) st_hint(sp - HDR, t, keep); // header of block T carries the final time
         if (own < n && !isfinite(x)) status |= VA_TRAJ_NONFINITE;
         fence_proxy_async(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
         status = slot_or(status);
@@ -389,6 +417,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                     for (int k = tid; k < npar; k += NTT) mu_o[k] = nan("");
                 continue;
             }
+            const uint64_t drop = policy_evict_first(); // last read of this parameter set by this seed
             // transposed tile: M[k][c] = A[FG(c)][8 hi + (k ^ g)]; the owned component stays `own`. A is re-read (L2 hit),
             // once per seed: the tile must not stay live across phase 3, whose accumulator needs its registers.
 #pragma unroll
@@ -397,8 +426,8 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int col = 8 * hi + (k ^ g);
-                    if (EXACT) M[k][c] = __ldg(pb + NP + row * NP + col);
-                    else M[k][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                    if (EXACT) M[k][c] = ldg_hint(pb + NP + row * NP + col, drop);
+                    else M[k][c] = (row < n && col < n) ? ldg_hint(pb + n + row * n + col, drop) : 0.0;
                 }
             }
             double lam;
@@ -412,7 +441,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 if (it < T) {
                     const int bi = it % NB;
                     mbar_expect_tx(&mbar[bi], xg_bytes);
-                    bulk_g2s(xg + bi * blk, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi]);
+                    bulk_g2s(xg + bi * blk, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi], keep);
                 }
             };
             slot_sync(); // every thread is past its reads of the buffers (previous seed / trajectory)
@@ -436,7 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 double v = W[SADJ] * bs[HDR + (SADJ - 1) * NP + own];
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
-                    gv[(m - 1) * NP] = v;
+                    st_hint(gv + (m - 1) * NP, v, keep);
                     double wg = 0.0, c1 = 0.0, c2 = 0.0;
                     const double sum = matvec(
                         M, v, m & 1,
@@ -478,11 +507,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                     const double *src = slab + (int64_t)(T - 1 - it) * blk;
                     if (vsep) {
                         mbar_expect_tx(&mbar[bi], (HDR + 2 * SADJ * NP) * 8);
-                        bulk_g2s(xg + bi * blk, src, (HDR + SADJ * NP) * 8, &mbar[bi]);
-                        bulk_g2s(xg + bi * blk + voff, src + voff, SADJ * NP * 8, &mbar[bi]);
+                        bulk_g2s(xg + bi * blk, src, (HDR + SADJ * NP) * 8, &mbar[bi], keep);
+                        bulk_g2s(xg + bi * blk + voff, src + voff, SADJ * NP * 8, &mbar[bi], keep);
                     } else {
                         mbar_expect_tx(&mbar[bi], xg_bytes);
-                        bulk_g2s(xg + bi * blk, src, xg_bytes, &mbar[bi]);
+                        bulk_g2s(xg + bi * blk, src, xg_bytes, &mbar[bi], keep);
                     }
                 }
             };
