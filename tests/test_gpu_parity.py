@@ -384,6 +384,37 @@ def test_glv_checkpoint_policy_recompute_matches_store_stages(va, N, B, stepper,
     assert_close(res[va.CKPT_RECOMPUTE]["mu"], res[va.CKPT_STORE_STAGES]["mu"], rtol=1e-11, what="mu, recompute vs store")
 
 
+@pytest.mark.parametrize("N,B", [(64, 5), (50, 3), (64, 1)])
+def test_glv_register_kernel_generations_agree(va, monkeypatch, N, B):
+    """33..64 species run on va_glv_t8.cu (64 threads per trajectory, 8x8 tiles, three phases); VA_GLV_V1 selects the
+    first-generation kernel (va_glv_wide.cu). Independent thread/data maps, same algorithm: cross-check them, with fewer
+    trajectories than slots in a CTA (idle slots), a non-padded and a padded species count, two seeds and the summed mode."""
+    p = oracle.synth_params(oracle.SYS_GLV, N, 909, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(1).standard_normal((B, 2, N))
+    res = []
+    for v1 in (False, True):
+        if v1:
+            monkeypatch.setenv("VA_GLV_V1", "1")
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=2) as e:
+            info = e.info()
+            assert info["kernel_family"] == 1 and info["threads_per_cta"] == (128 if v1 else 256)
+            r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+            s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+            z = e.forward_adjoint(x0, p, 2.0, 2.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)  # ti == tf: no step at all
+        assert (r["status"] == 0).all() and (z["n_accept"] == 0).all()
+        np.testing.assert_array_equal(z["x_final"], x0)
+        np.testing.assert_array_equal(z["lam"], seeds)
+        assert (z["mu"] == 0).all()
+        assert_close(s["mu"], r["mu"].sum(axis=0), rtol=1e-11, what="mu sum")
+        res.append(r)
+    a, b = res
+    np.testing.assert_array_equal(a["n_accept"], b["n_accept"])
+    assert_close(a["x_final"], b["x_final"], rtol=1e-12, what="x(tf)")
+    assert_close(a["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-11, what="lambda")
+    assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-11, what="mu")
+
+
 def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     """The two GLV kernel families are independent implementations: cross-check them at N = 64."""
     N, B = 64, 40

@@ -1,22 +1,25 @@
 // va_glv_t8.cu -- GLV forward + discrete-adjoint kernel for 33..64 species, second generation of the headline path
-//                  (GLV N = 64, one million parameter sets): 64 threads per trajectory, 8x8 register tiles, three phases.
+//                  (GLV N = 64, one million parameter sets): 64 threads per trajectory, 64-entry register tiles, three phases.
 //
 // f_i = x_i (r_i + (A x)_i), parameters [r, A row-major] (reference examples/GeneralizedLotkaVolterra/main.cpp:105-119).
 // Same algorithm as va_glv_wide.cu (reference lib/include/detail/runge_kutta.hpp:76-118 forward + odeint controlled
 // stepper; detail/backpropagation.hpp:83-158, 231-254 reverse); what changed is the thread <-> data map, chosen from
 // the ncu profile of the first generation (profiles/r01_glv64_ncu_full_ve.txt: FP64 pipe 48 % busy of which only 65 % were
 // the algorithmic DFMAs, 8 warps per SM, every stage a barrier -> loads -> DFMA -> exchange chain):
-//   * one CTA of 64 threads = one trajectory; the matrix is cut into 8x8 tiles of 8x8 entries (64 FP64 values = 128
-//     registers per thread). 8 loaded vector operands feed 64 DFMA (was 8 per 32), the partial sums are combined over
-//     8 lanes by select-free recursive halving (7 double shuffles), after which EVERY thread owns exactly one vector
-//     component: the stage recurrences are no longer computed redundantly (they were 2x redundant).
+//   * 64 threads = one trajectory (four trajectories per 256-thread CTA, one CTA per SM). The matrix is cut into tiles of
+//     64 entries per thread (128 registers): 4 rows x 16 columns by default (VA_T8_RT). 16 loaded vector operands feed
+//     64 DFMA, the four partial sums of a row are combined over 4 lanes in ONE round of 3 independent double shuffles
+//     (select-free: the tile is held permuted), after which EVERY thread owns exactly one vector component: the stage
+//     recurrences are no longer computed redundantly (they were 2x redundant). Measured: 8x8 tiles / 8 lanes / 7
+//     shuffles 5.65 M gradients/s, 4x16 / 4 lanes / 3 shuffles 5.94 M, 2x32 / 2 lanes 5.75 M.
 //   * the gradient accumulator Abar (another 128 registers) cannot be live next to the matrix, so the reverse sweep is
 //     split: phase 2 propagates lambda through the stored steps with A^T in registers and writes the seeds
 //     v_m = w_m o X_m to the step block in the slab; phase 3 streams the blocks once more and accumulates
 //     Abar += v_m X_m^T -- 64 independent DFMA chains per thread, no reductions, no barriers inside a step: pure FP64
-//     throughput that fills the pipe while other CTAs of the SM sit in their latency-bound phases.
-//   * <= 255 registers per thread, 4 CTAs = 8 warps per SM. (The register file is partitioned per SM sub-partition, so
-//     warps per SM come in multiples of four: the next step, 12 warps, leaves 168 registers and spills the tile.)
+//     throughput that fills the pipe while other trajectories of the SM sit in their latency-bound phases.
+//   * <= 255 registers per thread, 8 warps per SM. (The register file is partitioned per SM sub-partition, so warps per
+//     SM come in multiples of four: the next step, 12 warps, leaves 168 registers, serialises the operand loads and
+//     measured slower, 5.04 M.)
 // Step blocks: [8-double header (t_n) | X_0..X_{s-1} | g_0..g_{s-1} | v_1..v_s] in a private slab per CTA (reused for
 // every trajectory -> L2 resident), streamed back by TMA bulk copies (cp.async.bulk + mbarrier), NB buffers deep. With a
 // single seed per trajectory the v section aliases the g section (g_m is dead once v_m exists).
@@ -33,6 +36,12 @@
 #ifndef VA_T8_SLOTS
 #define VA_T8_SLOTS 4 // trajectories ("slots") per CTA: 4 -> one 256-thread CTA per SM; 1 -> 64-thread CTAs, VA_T8_MINB per SM
 #endif
+#ifndef VA_T8_RT
+#define VA_T8_RT 4 // rows of the matrix tile a thread holds in phases 1 and 2: 8 (8x8 tile, sums over 8 lanes) or 4 (4x16, 4 lanes)
+#endif
+#ifndef VA_T8_NC
+#define VA_T8_NC 1 // independent accumulator chains per tile row in a product (column pairs are dealt round-robin)
+#endif
 #ifndef VA_T8_NB
 #define VA_T8_NB 3 // step-block buffers per CTA
 #endif
@@ -47,6 +56,10 @@ constexpr int MINB = SLOTS == 1 ? VA_T8_MINB : 1;
 
 constexpr int HDR = 8;  // doubles in a step-block header (hdr[0] = t_n)
 constexpr int NB = VA_T8_NB;
+constexpr int RT = VA_T8_RT; // tile rows per thread = lanes per reduction group
+constexpr int CT = 64 / RT; // tile columns per thread
+constexpr int NC = VA_T8_NC;
+static_assert((RT == 8 || RT == 4 || RT == 2) && (NC == 1 || NC == 2 || NC == 4), "tile geometry");
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -158,9 +171,10 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     const int slot = SLOTS == 1 ? 0 : ((wc >> 2) << 1) | ((wc >> 1) & 1);
     const int warp = wc & 1;                       // warp inside the trajectory
     const int tid = warp * 32 + (threadIdx.x & 31); // thread inside the trajectory
-    const int g = tid & 7;   // lane inside the 8-lane reduction group
-    const int hi = tid >> 3; // reduction group 0..7
-    const int own = tid;     // vector component this thread owns after a reduction (8 hi + g)
+    const int g = tid & (RT - 1); // lane inside the reduction group (RT lanes)
+    const int hi = tid / RT;      // reduction group
+    const int own = tid;          // vector component this thread owns after a reduction (RT hi + g)
+    const int g8 = tid & 7, h8 = tid >> 3; // phase 3 keeps an 8x8 accumulator tile whatever RT is
     const int n = a.n;
     const int npar = n * n + n;
     const int cap = a.cap;
@@ -192,9 +206,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     // g-direction entries of a tile, as double2 offsets PO(j), j = 0..3: the 8 lanes of a group read 8 consecutive double2
     // (one conflict-free LDS.128, broadcast to the 4 groups of the warp). FG(e) = 2 PO(e>>1) + (e&1); FH is the same
     // pattern along the group index (phase 3 rows).
-    auto PO = [&](int j) { return g + 8 * j; };
+    auto PO = [&](int j) { return g + RT * j; };
     auto FG = [&](int e) { return 2 * PO(e >> 1) + (e & 1); };
-    auto FH = [&](int e) { return 2 * hi + (e & 1) + 16 * (e >> 1); };
+    auto PO8 = [&](int j) { return g8 + 8 * j; };
+    auto FG8 = [&](int e) { return 2 * PO8(e >> 1) + (e & 1); };
+    auto FH = [&](int e) { return 2 * h8 + (e & 1) + 16 * (e >> 1); };
 
     if (tid == 0) {
 #pragma unroll
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         for (int k = 0; k < 8; ++k)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const int row = FH(k), col = FG(c);
+                const int row = FH(k), col = FG8(c);
                 if (row < n && col < n) part[n + row * n + col] = 0.0;
             }
     }
@@ -222,55 +238,72 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     // shuffles and an add tree (recursive halving needs as many shuffles in three dependent rounds: measured 2.5 % slower).
     // `after_sync` runs right behind the barrier, `extra` between the DFMAs and the exchange (work that does not depend on
     // the result, off the critical path).
-    auto matvec = [&](const double(&M)[8][8], double X, int p, auto &&after_sync, auto &&extra) -> double {
+    // Besides the sum the product returns y = c1 * sum + c0 (c1, c0 are set by `extra`): the value the NEXT product needs.
+    // With four partial sums it is built as fma(c1, t2 + t3, fma(c1, t1, fma(c1, t0, c0))) -- two dependent operations behind
+    // the last shuffle instead of three.
+    auto matvec = [&](const double(&M)[RT][CT], double X, int p, auto &&after_sync, auto &&extra, const double &c1, const double &c0,
+                      double &y) -> double {
         xs[p][own] = X;
         slot_sync();
         after_sync();
         const double2 *xv = reinterpret_cast<const double2 *>(xs[p]);
-        double s[8];
-        {
-            const double2 v = xv[PO(0)];
+        double sc[NC][RT];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = M[k][0] * v.x;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = fma(M[k][1], v.y, s[k]);
-        }
-#pragma unroll
-        for (int j = 1; j < 4; ++j) {
+        for (int j = 0; j < CT / 2; ++j) {
             const double2 v = xv[PO(j)];
+            const int ch = j % NC;
+            if (j < NC) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = fma(M[k][2 * j], v.x, s[k]);
+                for (int k = 0; k < RT; ++k) sc[ch][k] = M[k][2 * j] * v.x;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = fma(M[k][2 * j + 1], v.y, s[k]);
+                for (int k = 0; k < RT; ++k) sc[ch][k] = fma(M[k][2 * j], v.x, sc[ch][k]);
+            }
+#pragma unroll
+            for (int k = 0; k < RT; ++k) sc[ch][k] = fma(M[k][2 * j + 1], v.y, sc[ch][k]);
         }
+        double s[RT];
+#pragma unroll
+        for (int k = 0; k < RT; ++k)
+            s[k] = NC == 1 ? sc[0][k] : NC == 2 ? sc[0][k] + sc[1 % NC][k] : (sc[0][k] + sc[1 % NC][k]) + (sc[2 % NC][k] + sc[3 % NC][k]);
         extra();
-        double t[8];
+        double t[RT];
         t[0] = s[0];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) t[j] = shx(s[j], j);
-        return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+        for (int j = 1; j < RT; ++j) t[j] = shx(s[j], j);
+        if (RT == 4) {
+            const double q = t[2 % RT] + t[3 % RT];
+            y = fma(c1, q, fma(c1, t[1], fma(c1, t[0], c0)));
+            return (t[0] + t[1]) + q;
+        }
+        const double sum = RT == 2 ? t[0] + t[1]
+                                   : ((t[0] + t[1]) + (t[2 % RT] + t[3 % RT])) + ((t[4 % RT] + t[5 % RT]) + (t[6 % RT] + t[7 % RT]));
+        y = fma(c1, sum, c0);
+        return sum;
     };
     auto nop = [] {};
+    const double zero = 0.0;
+    double ydummy;
 
     for (int64_t b = gslot; b < a.B; b += (int64_t)gridDim.x * SLOTS) {
         const double *pb = a.params + b * npar;
-        double M[8][8];
+        double M[RT][CT];
         // ================================ phase 1: forward sweep =====================================
-        // tile rows 8 hi + (k ^ g), columns FG(c)
+        // tile rows RT hi + (k ^ g), columns FG(c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int row = 8 * hi + (k ^ g);
+        for (int k = 0; k < RT; ++k) {
+            const int row = RT * hi + (k ^ g);
             if (EXACT) {
                 const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < CT / 2; ++j) {
                     const double2 v = __ldg(src + PO(j));
                     M[k][2 * j] = v.x;
                     M[k][2 * j + 1] = v.y;
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < CT; ++c) {
                     const int col = FG(c);
                     M[k][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
                 }
@@ -283,7 +316,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         int nck = 0, rejects = 0, status = 0, trials = 0;
         bool fresh = true;
         {
-            const double sum = matvec(M, x, 0, nop, nop);
+            const double sum = matvec(M, x, 0, nop, nop, zero, zero, ydummy);
             g0 = r_own + sum;
             K[0] = x * g0;
         }
@@ -309,6 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
             for (int m = 1; m < SE; ++m) {
                 const bool last = (m == SE - 1);
                 double c1 = 0.0, base = 0.0;
+                double Y;
                 const double sum = matvec(M, X, m & 1, nop, [&] {
                     double acc = 0.0;
 #pragma unroll
@@ -324,8 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                         for (int j = 0; j < m; ++j)
                             if (Tab::db(j) != 0.0) perr = fma(a.coef.db[j], K[j], perr);
                     }
-                });
-                const double Y = fma(c1, sum, base);
+                }, c1, base, Y);
                 const double gg = r_own + sum;
                 K[m] = X * gg;
                 if (m < SADJ) { st_hint(sp + m * NP, X, keep); st_hint(sp + (SADJ + m) * NP, gg, keep); }
@@ -348,7 +381,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 if ((tid & 31) == 0) red[warp] = e;
             };
             if (ERR_EARLY) err_local();
-            const double gl = r_own + matvec(M, X, SE & 1, nop, nop);
+            const double gl = r_own + matvec(M, X, SE & 1, nop, nop, zero, zero, ydummy);
             const double Kl = X * gl;
             if (Tab::FSAL) K[S - 1] = Kl;
             double err = 0.0;
@@ -418,14 +451,14 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 continue;
             }
             const uint64_t drop = policy_evict_first(); // last read of this parameter set by this seed
-            // transposed tile: M[k][c] = A[FG(c)][8 hi + (k ^ g)]; the owned component stays `own`. A is re-read (L2 hit),
+            // transposed tile: M[k][c] = A[FG(c)][RT hi + (k ^ g)]; the owned component stays `own`. A is re-read (L2 hit),
             // once per seed: the tile must not stay live across phase 3, whose accumulator needs its registers.
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < CT; ++c) {
                 const int row = FG(c);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int col = 8 * hi + (k ^ g);
+                for (int k = 0; k < RT; ++k) {
+                    const int col = RT * hi + (k ^ g);
                     if (EXACT) M[k][c] = ldg_hint(pb + NP + row * NP + col, drop);
                     else M[k][c] = (row < n && col < n) ? ldg_hint(pb + n + row * n + col, drop) : 0.0;
                 }
@@ -467,6 +500,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 for (int m = SADJ; m >= 1; --m) {
                     st_hint(gv + (m - 1) * NP, v, keep);
                     double wg = 0.0, c1 = 0.0, c2 = 0.0;
+                    double v_next;
                     const double sum = matvec(
                         M, v, m & 1,
                         [&] {
@@ -482,8 +516,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                                 if (Tab::a(m - 1, m - 2) != 0.0) c1 = (a.coef.a[m - 1][m - 2] * dt_s) * Xn;
                                 c2 = fma(wg, c1, W[m - 1] * Xn);
                             }
-                        });
-                    const double v_next = fma(sum, c1, c2);
+                        }, c1, c2, v_next);
                     const double gx = sum + wg;
                     const double gxd = gx * dt_s;
                     rbar += v;
@@ -531,12 +564,12 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 const double *bs = xg + bi * blk;
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
-                    const double2 *vv = reinterpret_cast<const double2 *>(bs + voff + (m - 1) * NP) + hi;
+                    const double2 *vv = reinterpret_cast<const double2 *>(bs + voff + (m - 1) * NP) + h8;
                     const double2 *xx = reinterpret_cast<const double2 *>(bs + HDR + (m - 1) * NP);
                     double vr[8], xc[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const double2 p = vv[8 * j], q = xx[PO(j)];
+                        const double2 p = vv[8 * j], q = xx[PO8(j)];
                         vr[2 * j] = p.x; vr[2 * j + 1] = p.y;
                         xc[2 * j] = q.x; xc[2 * j + 1] = q.y;
                     }
@@ -554,11 +587,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                     if (EXACT) {
                         double2 *dst = reinterpret_cast<double2 *>(mu_o + NP + row * NP);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[PO(j)] = make_double2(Ab[k][2 * j], Ab[k][2 * j + 1]);
+                        for (int j = 0; j < 4; ++j) dst[PO8(j)] = make_double2(Ab[k][2 * j], Ab[k][2 * j + 1]);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const int col = FG(c);
+                            const int col = FG8(c);
                             if (row < n && col < n) mu_o[n + row * n + col] = Ab[k][c];
                         }
                     }
@@ -571,7 +604,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 for (int k = 0; k < 8; ++k)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const int row = FH(k), col = FG(c);
+                        const int row = FH(k), col = FG8(c);
                         if (row < n && col < n) atomicAdd(part + n + row * n + col, Ab[k][c]);
                     }
             }
