@@ -1,1 +1,1 @@
-timeout 300 python -m pytest tests -m gpu -x -q -k "glv" 2>&1 | tail -1; for i in 1 2; do timeout 200 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'])"; done
+for tool in memcheck racecheck; do echo "== $tool"; timeout 800 compute-sanitizer --tool $tool --print-limit 3 python tools/sanitize.py 2>&1 | grep -v "^$" | tail -9; done

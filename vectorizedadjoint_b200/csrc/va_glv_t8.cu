@@ -305,12 +305,22 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 #pragma unroll
                 for (int c = 0; c < CT; ++c) {
                     const int col = FG(c);
-                    M[k][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                    {
+                        // padded entries: the load goes to a valid address and is discarded (the compiler may turn a guarded
+                        // load into load + select, which must not leave the parameter block)
+                        const bool in = row < n && col < n;
+                        const double v = __ldg(pb + n + (in ? row * n + col : 0));
+                        M[k][c] = in ? v : 0.0;
+                    }
                 }
             }
         }
         double r_own = 0.0, x = 0.0;
-        if (own < n) { r_own = __ldg(pb + own); x = __ldg(a.x0 + b * n + own); }
+        {
+            const int oi = own < n ? own : 0; // padded lanes read a valid address and discard it
+            const double rv = __ldg(pb + oi), xv0 = __ldg(a.x0 + b * n + oi);
+            if (own < n) { r_own = rv; x = xv0; }
+        }
 
         double t = a.ti, dt = a.dt0, K[S], g0;
         int nck = 0, rejects = 0, status = 0, trials = 0;
@@ -460,13 +470,17 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 for (int k = 0; k < RT; ++k) {
                     const int col = RT * hi + (k ^ g);
                     if (EXACT) M[k][c] = ldg_hint(pb + NP + row * NP + col, drop);
-                    else M[k][c] = (row < n && col < n) ? ldg_hint(pb + n + row * n + col, drop) : 0.0;
+                    else {
+                        const bool in = row < n && col < n;
+                        const double v = ldg_hint(pb + n + (in ? row * n + col : 0), drop);
+                        M[k][c] = in ? v : 0.0;
+                    }
                 }
             }
             double lam;
             if (a.objective == VA_OBJ_SUM) lam = (own < n) ? 1.0 : 0.0;
             else if (a.objective == VA_OBJ_HALF_NORM2) lam = x_tf;
-            else lam = (own < n) ? lam_io[own] : 0.0;
+            else lam = (own < n) ? lam_io[own < n ? own : 0] : 0.0;
             double rbar = 0.0;
 
             // stream the step blocks back, newest first: iteration it <-> step T-1-it, buffer it % NB, NB-1 blocks ahead

@@ -228,7 +228,12 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
 #pragma unroll
                     for (int c = 0; c < TG; ++c) {
                         const int col = FG(c);
-                        Af[q][r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                        {
+                            // padded entries load a valid address and are discarded (a guarded load may become load + select)
+                            const bool in = row < n && col < n;
+                            const double v = __ldg(pb + n + (in ? row * n + col : 0));
+                            Af[q][r][c] = in ? v : 0.0;
+                        }
                     }
                 }
             }
@@ -239,7 +244,11 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
                 cswap(sw_hi, Af[q][0][c], Af[q][2][c]);
                 cswap(sw_hi, Af[q][1][c], Af[q][3][c]);
             }
-            if (ex[q] && own < n) { r_own[q] = __ldg(pb + own); x[q] = __ldg(a.x0 + bq[q] * n + own); }
+            {
+                const int oi = own < n ? own : 0; // padded lanes read a valid address and discard it
+                const double rv = __ldg(pb + oi), xv0 = __ldg(a.x0 + (ex[q] ? bq[q] : b0) * n + oi);
+                if (ex[q] && own < n) { r_own[q] = rv; x[q] = xv0; }
+            }
         }
 
         // sum[q] = (A_q X_q)_own for the stage states whose own-components are X[q]. `extra` runs between the operand
@@ -514,7 +523,11 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int col = 4 * hi + c;
-                        Ab[r][c] = (row < n && col < n) ? __ldg(pb + n + row * n + col) : 0.0;
+                        {
+                            const bool in = row < n && col < n;
+                            const double v = __ldg(pb + n + (in ? row * n + col : 0));
+                            Ab[r][c] = in ? v : 0.0;
+                        }
                     }
                 }
             }
@@ -539,7 +552,7 @@ __global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5
             double lam;
             if (a.objective == VA_OBJ_SUM) lam = (own < n) ? 1.0 : 0.0;
             else if (a.objective == VA_OBJ_HALF_NORM2) lam = x_tf;
-            else lam = (own < n) ? lam_io[own] : 0.0;
+            else lam = (own < n) ? lam_io[own < n ? own : 0] : 0.0;
 
             if (a.reduce == VA_REDUCE_NONE) {
 #pragma unroll
