@@ -40,7 +40,7 @@ WORKLOADS = {
     "glv16": (2, 16, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
               "GLV N=16 (Npar=272), 2^20 parameter sets, cash_karp54 controlled rtol=atol=1e-8, t=[0,10], full r and A gradient"),
     "glv256": (2, 256, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
-               "GLV N=256 (Npar=65792), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; streamed-matrix kernel family; default batch 8192"),
+               "GLV N=256 (Npar=65792), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; ring-streamed kernel (va_glv_ring.cu: TMA ring of 32 KB matrix chunks, 64 rows cached in registers); default batch 8192"),
     "vdp": (1, 2, 3, True, 1e-8, 0.0, 0.5, 1e-3, 1024, 1, 7,
             "Van der Pol, mu swept over [1,1024), 2^20 parameter sets, dopri5 controlled rtol=atol=1e-8, t=[0,0.5], dt0=1e-3"),
     "harmonic": (0, 2, 1, False, 0.0, 0.0, 10.0, 0.01, 1024, 2, 4,
@@ -261,6 +261,20 @@ def side_workload(args):
         peak = va.measure_fp64_peak(0)
         line["roofline"] = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                             "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None}
+        if n == 256 and info["ctas_per_sm"] == 1:
+            # ring-streamed kernel: every matrix-vector product re-reads the non-cached rows of the 512 KB matrix from L2/HBM
+            cached = 0 if (int(os.environ.get("VA_RING_FLAGS", "2")) & 4) else 64
+            products = (stages * T + (stages - 1) * R) + stages * T + B
+            sbytes = products * (n - cached) * n * 8
+            hbm = None
+            try:
+                hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            except Exception:
+                pass
+            line["roofline"]["matrix_stream"] = {"products": products, "bytes_per_product": (n - cached) * n * 8,
+                                                 "achieved_gbs": sbytes / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
+                                                 "note": "matrix chunks streamed by TMA per product; source is L2 when the matrices of the "
+                                                         "resident CTAs (148 x 512 KB) stay resident, HBM otherwise"}
     else:
         # thread-per-trajectory family: compulsory HBM bytes are the checkpoints, written by the forward kernel and read back
         # by the reverse kernel: 2 * 8 * (N+1) * (T + B) bytes (+ inputs/outputs)

@@ -437,6 +437,76 @@ def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     np.testing.assert_array_equal(x[0], x0[3])
 
 
+@pytest.mark.parametrize("flags", ["2", "0", "6"])
+def test_glv256_ring_kernel_agrees_with_streamed_kernel_and_oracle(va, monkeypatch, flags):
+    """256 species, store-stages policy: served by the ring-streamed kernel (va_glv_ring.cu: TMA ring of matrix chunks,
+    64 rows cached in registers, gradient accumulation as a matrix product). VA_GLV_NO_RING selects the plain streamed
+    kernel (va_glv_stream.cu), an independent thread/data map of the same algorithm. More trajectories than one CTA wave
+    would need at B = 150 is too slow for the oracle, so: a few sets against the oracle, two seeds per trajectory, summed
+    mode, the J = |x|^2/2 objective, ti == tf, and both kernels against each other. VA_RING_FLAGS: bit 1 = evict_last
+    matrix stream, bit 2 = no register-cached rows."""
+    N, B = 256, 5
+    p = oracle.synth_params(oracle.SYS_GLV, N, 4242, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(7).standard_normal((B, 2, N))
+    monkeypatch.setenv("VA_RING_FLAGS", flags)
+    res = []
+    for ring in (True, False):
+        if not ring:
+            monkeypatch.setenv("VA_GLV_NO_RING", "1")
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=2) as e:
+            info = e.info()
+            assert info["kernel_family"] == 2 and info["ctas_per_sm"] == (1 if ring else 2)
+            r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+            s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+            z = e.forward_adjoint(x0, p, 2.0, 2.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)  # ti == tf: no step at all
+            e.forward(x0, p, 0.0, 10.0, 1e-3)
+            t, x = e.checkpoints(2)
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+            h = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2)
+            hs = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2, reduce=va.REDUCE_SUM)
+        assert (r["status"] == 0).all() and (z["n_accept"] == 0).all()
+        np.testing.assert_array_equal(z["x_final"], x0)
+        np.testing.assert_array_equal(z["lam"], seeds)
+        assert (z["mu"] == 0).all()
+        assert_close(s["mu"], r["mu"].sum(axis=0), rtol=1e-11, what="mu sum")
+        assert_close(hs["mu"], h["mu"].sum(axis=0), rtol=1e-11, what="mu sum (native summed mode)")
+        assert len(t) == r["n_accept"][2] + 1 and t[0] == 0.0
+        np.testing.assert_array_equal(x[0], x0[2])
+        res.append((r, h))
+    (a, ha), (b, hb) = res
+    np.testing.assert_array_equal(a["n_accept"], b["n_accept"])
+    assert_close(a["x_final"], b["x_final"], rtol=1e-12, what="x(tf)")
+    assert_close(a["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-10, what="lambda")
+    assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-10, what="mu")
+    assert_close(ha["mu"][:, 0], hb["mu"][:, 0], rtol=1e-10, what="mu, half-norm objective")
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0, p, 0.0, 10.0, 1e-3,
+                               objective=oracle.OBJ_HALF_NORM2, threads=8)
+    np.testing.assert_array_equal(ha["n_accept"], o["n_accept"])
+    assert_close(ha["x_final"], o["x_final"], what="x(tf)")
+    assert_close(ha["lam"][:, 0], o["lam"], what="lambda")
+    assert_close(ha["mu"][:, 0], o["mu"], what="mu")
+
+
+def test_glv256_ring_kernel_many_waves_summed_mode(va):
+    """More trajectories than resident CTAs (every CTA integrates several trajectories and keeps adding to its partial-sum
+    row): the summed gradient equals the sum of the per-trajectory gradients, and a replicated parameter set gives
+    identical rows."""
+    N, B = 256, 400
+    base = oracle.synth_params(oracle.SYS_GLV, N, 99, 0, 3)
+    p = base[np.arange(B) % 3]
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        assert e.info()["ctas_per_sm"] == 1
+        r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+        s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+    assert (r["status"] == 0).all()
+    for k in range(3):
+        np.testing.assert_array_equal(r["mu"][k::3], np.broadcast_to(r["mu"][k], r["mu"][k::3].shape))
+        np.testing.assert_array_equal(r["x_final"][k::3], np.broadcast_to(r["x_final"][k], r["x_final"][k::3].shape))
+    assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
+
+
 def test_backward_in_time_integration(va):
     """dt0 < 0 (tf < ti): odeint's less_with_sign logic is sign-aware (reference lib/include/detail/runge_kutta.hpp:93,98)."""
     B = 64

@@ -47,6 +47,13 @@ bool va_glv_stream_supported(int n, int stepper, int adaptive);
 int va_glv_stream_block_doubles(int n, int stepper, int recompute);
 cudaError_t va_glv_stream_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
+// ring-streamed GLV kernel for 256 species (va_glv_ring.cu): one 256-thread CTA per SM, matrix streamed through a TMA ring,
+// store-stages policy; a.recompute carries its flag word (bit 1: evict_last matrix stream, bit 2: no register-cached rows)
+bool va_glv_ring_supported(int n, int stepper, int adaptive);
+int va_glv_ring_block_doubles(int stepper);
+size_t va_glv_ring_smem();
+cudaError_t va_glv_ring_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
 // out[k] (+)= sum_{g<G} in[g*stride + k], deterministic order
 cudaError_t va_reduce_rows(const double *in, int64_t G, int64_t stride, int64_t n, double *out, int accumulate, cudaStream_t st);
 

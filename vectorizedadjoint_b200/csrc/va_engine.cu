@@ -81,6 +81,8 @@ struct va_engine {
     int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
     bool t8 = false;  // FAM_GLV_WIDE served by va_glv_t8.cu (33..64 species)
     int glv_blk = 0;  // doubles per step block of the register-kernel slab
+    bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
+    int ring_flags = 0;
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -227,7 +229,10 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         }
         if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
-        else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
+        else if (e->ring) {
+            a.recompute = e->ring_flags;
+            VA_CUDA(va_glv_ring_forward_adjoint(a, st));
+        } else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
         ++e->launches;
         if (native_sum) {
             VA_CUDA(va_reduce_rows(e->partial.as<double>(), (int64_t)a.grid * e->tpc, npar, npar, d.mu, d.mu_accumulate ? 1 : 0, st));
@@ -471,6 +476,23 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         }
         e->desc.ckpt_policy = policy;
         e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, policy == VA_CKPT_RECOMPUTE);
+        // 256 species, store-stages: the ring-streamed kernel (va_glv_ring.cu); VA_GLV_NO_RING keeps the plain streamed kernel
+        e->ring = policy == VA_CKPT_STORE_STAGES && va_glv_ring_supported(desc->n_state, desc->stepper, desc->adaptive) &&
+                  !getenv("VA_GLV_NO_RING");
+        if (e->ring) {
+            e->ctas_per_sm = 1;
+            e->grid = e->sm_count;
+            e->glv_blk = va_glv_ring_block_doubles(desc->stepper);
+            e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+            // the matrices of all resident CTAs (148 x 512 KB) are re-read for every product: keep them in L2 (evict_last class,
+            // persisting carve-out at the device maximum); VA_RING_FLAGS overrides (bit 1: evict_last, bit 2: no cached rows)
+            e->ring_flags = getenv("VA_RING_FLAGS") ? atoi(getenv("VA_RING_FLAGS")) : 2;
+            if (e->ring_flags & 2) {
+                int max_persist = 0;
+                if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device) == cudaSuccess && max_persist > 0)
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            }
+        }
     } else if (family == FAM_GLV_WIDE) {
         // 33..64 species: second-generation kernel (va_glv_t8.cu); VA_GLV_V1 keeps the first generation for cross-checks
         e->t8 = va_glv_t8_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_V1");
@@ -693,7 +715,7 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
         const double *base = e->slab.as<double>() + b * e->pair * e->slab_stride; // first wave: trajectory b = slot b, slab 0
-        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE ? e->glv_blk
+        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE || e->ring ? e->glv_blk
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {
