@@ -40,7 +40,7 @@ WORKLOADS = {
     "glv16": (2, 16, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
               "GLV N=16 (Npar=272), 2^20 parameter sets, cash_karp54 controlled rtol=atol=1e-8, t=[0,10], full r and A gradient"),
     "glv256": (2, 256, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
-               "GLV N=256 (Npar=65792), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; ring-streamed kernel (va_glv_ring.cu: TMA ring of 32 KB matrix chunks, 64 rows cached in registers); default batch 8192"),
+               "GLV N=256 (Npar=65792), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; cluster-pair kernel (va_glv_pair.cu: matrix on chip in two SMs; VA_GLV_NO_PAIR=1: ring-streamed kernel va_glv_ring.cu); default batch 8192"),
     "vdp": (1, 2, 3, True, 1e-8, 0.0, 0.5, 1e-3, 1024, 1, 7,
             "Van der Pol, mu swept over [1,1024), 2^20 parameter sets, dopri5 controlled rtol=atol=1e-8, t=[0,0.5], dt0=1e-3"),
     "harmonic": (0, 2, 1, False, 0.0, 0.0, 10.0, 0.01, 1024, 2, 4,
@@ -261,7 +261,8 @@ def side_workload(args):
         peak = va.measure_fp64_peak(0)
         line["roofline"] = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                             "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None}
-        if n == 256 and info["ctas_per_sm"] == 1:
+        line["kernel"] = info.get("kernel_name")
+        if n == 256 and info.get("kernel_name") == "k_glv_ring":
             # ring-streamed kernel: every matrix-vector product re-reads the non-cached rows of the 512 KB matrix from L2/HBM
             cached = 0 if (int(os.environ.get("VA_RING_FLAGS", "2")) & 4) else 64
             products = (stages * T + (stages - 1) * R) + stages * T + B

@@ -111,6 +111,8 @@ typedef struct va_engine_info {
     int64_t kernel_launches; /* launches of this library's kernels since creation                                */
     double last_kernel_ms;   /* device time of the last fused/forward/adjoint call (CUDA events on its stream)   */
     char device_name[64];
+    char kernel_name[32];    /* the kernel that serves this engine: k_scalar, k_glv_wide, k_glv_t8, k_glv_stream, k_glv_ring,
+                                k_glv_pair, or jit (run-time compiled thread-per-trajectory kernels of a recorded system)  */
 } va_engine_info;
 
 #ifndef __CUDACC_RTC__ /* the enums and structs above are also seen by run-time compiled device code */

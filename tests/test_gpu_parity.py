@@ -437,26 +437,29 @@ def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     np.testing.assert_array_equal(x[0], x0[3])
 
 
-@pytest.mark.parametrize("flags", ["2", "0", "6"])
-def test_glv256_ring_kernel_agrees_with_streamed_kernel_and_oracle(va, monkeypatch, flags):
-    """256 species, store-stages policy: served by the ring-streamed kernel (va_glv_ring.cu: TMA ring of matrix chunks,
-    64 rows cached in registers, gradient accumulation as a matrix product). VA_GLV_NO_RING selects the plain streamed
-    kernel (va_glv_stream.cu), an independent thread/data map of the same algorithm. More trajectories than one CTA wave
-    would need at B = 150 is too slow for the oracle, so: a few sets against the oracle, two seeds per trajectory, summed
-    mode, the J = |x|^2/2 objective, ti == tf, and both kernels against each other. VA_RING_FLAGS: bit 1 = evict_last
-    matrix stream, bit 2 = no register-cached rows."""
+@pytest.mark.parametrize("kernel", ["k_glv_pair", "k_glv_ring:2", "k_glv_ring:0", "k_glv_ring:6"])
+def test_glv256_onchip_and_ring_kernels_agree_with_streamed_kernel_and_oracle(va, monkeypatch, kernel):
+    """256 species, store-stages policy. Three independent thread/data maps of the same algorithm:
+    k_glv_pair (va_glv_pair.cu, default: two CTAs of a cluster hold the matrix on chip and exchange product halves through
+    distributed shared memory), k_glv_ring (va_glv_ring.cu, VA_GLV_NO_PAIR: TMA ring of matrix chunks, 64 rows cached in
+    registers; VA_RING_FLAGS bit 1 = evict_last matrix stream, bit 2 = no register-cached rows) and k_glv_stream
+    (va_glv_stream.cu, VA_GLV_NO_RING). A few sets against the oracle, two seeds per trajectory, summed mode, the
+    J = |x|^2/2 objective, ti == tf, checkpoints, and the kernels against each other."""
     N, B = 256, 5
     p = oracle.synth_params(oracle.SYS_GLV, N, 4242, 0, B)
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
     seeds = np.random.default_rng(7).standard_normal((B, 2, N))
-    monkeypatch.setenv("VA_RING_FLAGS", flags)
+    name, _, flags = kernel.partition(":")
+    if name == "k_glv_ring":
+        monkeypatch.setenv("VA_GLV_NO_PAIR", "1")
+        monkeypatch.setenv("VA_RING_FLAGS", flags)
     res = []
-    for ring in (True, False):
-        if not ring:
+    for fast in (True, False):
+        if not fast:
             monkeypatch.setenv("VA_GLV_NO_RING", "1")
         with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=2) as e:
             info = e.info()
-            assert info["kernel_family"] == 2 and info["ctas_per_sm"] == (1 if ring else 2)
+            assert info["kernel_family"] == 2 and info["kernel_name"] == (name if fast else "k_glv_stream")
             r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
             s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
             z = e.forward_adjoint(x0, p, 2.0, 2.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)  # ti == tf: no step at all
@@ -488,16 +491,19 @@ def test_glv256_ring_kernel_agrees_with_streamed_kernel_and_oracle(va, monkeypat
     assert_close(ha["mu"][:, 0], o["mu"], what="mu")
 
 
-def test_glv256_ring_kernel_many_waves_summed_mode(va):
-    """More trajectories than resident CTAs (every CTA integrates several trajectories and keeps adding to its partial-sum
-    row): the summed gradient equals the sum of the per-trajectory gradients, and a replicated parameter set gives
-    identical rows."""
+@pytest.mark.parametrize("kernel", ["k_glv_pair", "k_glv_ring"])
+def test_glv256_many_waves_summed_mode(va, monkeypatch, kernel):
+    """More trajectories than resident CTAs / CTA pairs (each integrates several trajectories and keeps adding to its
+    partial-sum row): the summed gradient equals the sum of the per-trajectory gradients, and a replicated parameter set
+    gives identical rows."""
+    if kernel == "k_glv_ring":
+        monkeypatch.setenv("VA_GLV_NO_PAIR", "1")
     N, B = 256, 400
     base = oracle.synth_params(oracle.SYS_GLV, N, 99, 0, 3)
     p = base[np.arange(B) % 3]
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
     with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
-        assert e.info()["ctas_per_sm"] == 1
+        assert e.info()["kernel_name"] == kernel
         r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
         s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
     assert (r["status"] == 0).all()

@@ -61,7 +61,8 @@ class _Info(ctypes.Structure):
     _fields_ = [("api_version", ctypes.c_int32), ("device", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("kernel_family", ctypes.c_int32),
                 ("ckpt_policy", ctypes.c_int32), ("max_steps", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32),
                 ("threads_per_cta", ctypes.c_int32), ("workspace_bytes", ctypes.c_int64), ("chunk_trajectories", ctypes.c_int64),
-                ("kernel_launches", ctypes.c_int64), ("last_kernel_ms", ctypes.c_double), ("device_name", ctypes.c_char * 64)]
+                ("kernel_launches", ctypes.c_int64), ("last_kernel_ms", ctypes.c_double), ("device_name", ctypes.c_char * 64),
+                ("kernel_name", ctypes.c_char * 32)]
 
 
 def build(verbose: bool = False) -> str:
@@ -166,6 +167,7 @@ class Engine:
         _check(lib().va_engine_get_info(self._h, ctypes.byref(i)), "va_engine_get_info")
         d = {k: getattr(i, k) for k, _ in _Info._fields_}
         d["device_name"] = i.device_name.decode()
+        d["kernel_name"] = i.kernel_name.decode()
         return d
 
     # ---- raw call: caller-provided buffers (numpy = host memory, torch.cuda = device memory) ----------------------

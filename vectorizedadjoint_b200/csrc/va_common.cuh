@@ -54,6 +54,13 @@ int va_glv_ring_block_doubles(int stepper);
 size_t va_glv_ring_smem();
 cudaError_t va_glv_ring_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
+// cluster-pair GLV kernel for 256 species (va_glv_pair.cu): two CTAs (a 2 x 1 x 1 cluster) per trajectory hold the matrix on
+// chip (registers + shared memory) and exchange product halves through distributed shared memory; a.grid must be even
+bool va_glv_pair_supported(int n, int stepper, int adaptive);
+int va_glv_pair_block_doubles(int stepper);
+size_t va_glv_pair_smem();
+cudaError_t va_glv_pair_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
 // out[k] (+)= sum_{g<G} in[g*stride + k], deterministic order
 cudaError_t va_reduce_rows(const double *in, int64_t G, int64_t stride, int64_t n, double *out, int accumulate, cudaStream_t st);
 

@@ -83,6 +83,7 @@ struct va_engine {
     int glv_blk = 0;  // doubles per step block of the register-kernel slab
     bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
     int ring_flags = 0;
+    bool pairk = false; // FAM_GLV_STREAM served by va_glv_pair.cu (256 species, matrix on chip in a 2-CTA cluster)
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -215,6 +216,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.n_accept = acc; a.n_reject = rej; a.status = sta;
         a.slab = e->slab.as<double>(); a.slab_stride = e->slab_stride; a.partial = e->partial.as<double>();
         a.grid = (int)std::min<int64_t>(e->grid, (d.B + e->tpc - 1) / e->tpc);
+        if (e->pairk) a.grid = 2 * (int)std::min<int64_t>(e->grid / 2, d.B); // two CTAs per trajectory
         a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE;
         a.blk_doubles = e->glv_blk;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
@@ -229,13 +231,15 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         }
         if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
+        else if (e->pairk) VA_CUDA(va_glv_pair_forward_adjoint(a, st));
         else if (e->ring) {
             a.recompute = e->ring_flags;
             VA_CUDA(va_glv_ring_forward_adjoint(a, st));
         } else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
         ++e->launches;
         if (native_sum) {
-            VA_CUDA(va_reduce_rows(e->partial.as<double>(), (int64_t)a.grid * e->tpc, npar, npar, d.mu, d.mu_accumulate ? 1 : 0, st));
+            VA_CUDA(va_reduce_rows(e->partial.as<double>(), e->pairk ? a.grid / 2 : (int64_t)a.grid * e->tpc, npar, npar, d.mu,
+                                   d.mu_accumulate ? 1 : 0, st));
             ++e->launches;
         } else if (sum && !d.forward_only) {
             VA_CUDA(va_reduce_rows(e->mu_tmp.as<double>(), d.B, (int64_t)nout * npar, (int64_t)nout * npar, d.mu,
@@ -477,8 +481,18 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         e->desc.ckpt_policy = policy;
         e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, policy == VA_CKPT_RECOMPUTE);
         // 256 species, store-stages: the ring-streamed kernel (va_glv_ring.cu); VA_GLV_NO_RING keeps the plain streamed kernel
-        e->ring = policy == VA_CKPT_STORE_STAGES && va_glv_ring_supported(desc->n_state, desc->stepper, desc->adaptive) &&
+        // 256 species, store-stages: the cluster-pair kernel (va_glv_pair.cu, matrix on chip); VA_GLV_NO_PAIR selects the
+        // ring-streamed kernel, VA_GLV_NO_RING the plain streamed kernel
+        e->pairk = policy == VA_CKPT_STORE_STAGES && va_glv_pair_supported(desc->n_state, desc->stepper, desc->adaptive) &&
+                   !getenv("VA_GLV_NO_PAIR") && !getenv("VA_GLV_NO_RING") && e->sm_count >= 2;
+        e->ring = !e->pairk && policy == VA_CKPT_STORE_STAGES && va_glv_ring_supported(desc->n_state, desc->stepper, desc->adaptive) &&
                   !getenv("VA_GLV_NO_RING");
+        if (e->pairk) {
+            e->ctas_per_sm = 1;
+            e->grid = e->sm_count / 2 * 2;
+            e->glv_blk = va_glv_pair_block_doubles(desc->stepper);
+            e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+        }
         if (e->ring) {
             e->ctas_per_sm = 1;
             e->grid = e->sm_count;
@@ -570,6 +584,9 @@ int va_engine_get_info(va_engine *e, va_engine_info *info)
     info->chunk_trajectories = e->chunk_traj;
     info->kernel_launches = e->launches;
     info->last_kernel_ms = e->last_ms;
+    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->t8 ? "k_glv_t8" : "k_glv_wide")
+                     : e->pairk ? "k_glv_pair" : e->ring ? "k_glv_ring" : "k_glv_stream";
+    std::snprintf(info->kernel_name, sizeof(info->kernel_name), "%s", kn);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) std::snprintf(info->device_name, sizeof(info->device_name), "%s", prop.name);
     return VA_OK;
@@ -714,8 +731,9 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     } else {
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
-        const double *base = e->slab.as<double>() + b * e->pair * e->slab_stride; // first wave: trajectory b = slot b, slab 0
-        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE || e->ring ? e->glv_blk
+        // first wave: trajectory b = slot b, slab 0 (cluster-pair kernel: CTA 2b of pair b)
+        const double *base = e->slab.as<double>() + b * (e->pairk ? 2 : e->pair) * e->slab_stride;
+        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE || e->ring || e->pairk ? e->glv_blk
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {

@@ -1,0 +1,555 @@
+// va_glv_pair.cu -- Generalized Lotka-Volterra with 256 species (BASELINE config 5) with the 512 KB interaction matrix
+// held ON CHIP by a thread-block cluster of two CTAs (two SMs) per trajectory: CTA `rank` owns rows
+// [128 rank, 128 rank + 128) of A -- 64 of them in shared memory (128 KB, loaded once per trajectory by TMA bulk copies),
+// 64 in registers (128 registers per thread) -- so no matrix byte is re-read from L2/HBM during a sweep. The ring-streamed
+// kernel (va_glv_ring.cu) is bound by the L2 -> SM path (11 TB/s of matrix chunks); this one exchanges 2 KB per product
+// through distributed shared memory instead.
+//
+// Both CTAs of a pair run the same program on the same values (thread i of either CTA owns component i of every vector;
+// state, stage slopes and stage adjoints live in registers; the controller's decisions are bitwise identical), and meet
+// once per matrix-vector product:
+//   g = r + A X   : a CTA computes its 128 rows (row dot products: lanes stride over the columns, transposing shuffle
+//                   reduction), stores them into its own AND the partner's result vector (st through map_shared_rank),
+//                   then one cluster barrier;
+//   A^T v         : a CTA sums over its 128 rows for all 256 columns (thread j owns column j: no reduction), stores the
+//                   partial sum into the partner's buffer, one cluster barrier, then own + partner's (commutative: both CTAs
+//                   get the same bits).
+// Result and partial-sum buffers are double-buffered by product parity, so a fast CTA can start the next product while the
+// partner still reads the last one.
+//
+// Same algorithm and phases as va_glv_ring.cu (reference lib/include/detail/runge_kutta.hpp:76-118 forward sweep with
+// odeint's controlled stepper, detail/backpropagation.hpp:83-158, 231-254 reverse sweep; store-stages policy: every accepted
+// step leaves a block [8-double header (t_n) | X_0.. | g_0.. | v_0..] in the CTA's slab): 1. forward sweep, 2. state adjoint,
+// 3. gradient accumulation Abar = sum_k v_k X_k^T as a matrix product with 8 x 8 accumulators per thread -- each CTA of the
+// pair takes two of the four 64-column passes.
+#include <cooperative_groups.h>
+
+#include "va_glv_common.cuh"
+#include "va_tma.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+using namespace va_tma;
+
+constexpr int NT = 256;        // threads per CTA
+constexpr int N = 256;         // species: thread i owns component i
+constexpr int HR = N / 2;      // matrix rows per CTA
+constexpr int SR = 64;         // ... of which in shared memory (own rows [0, SR))
+constexpr int CR = HR - SR;    // ... and in registers (own rows [SR, HR))
+constexpr int PCOLS = 64;      // columns of Abar per accumulation pass
+constexpr int SADJ_MAX = 6;
+constexpr uint32_t TMA_PIECE = 32768;
+static_assert(N == NT && CR == 64 && SR % 8 == 0 && (SR * N * 8) % TMA_PIECE == 0, "geometry");
+
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// sums of 8 values over the 32 lanes with 4 + 2 + 1 + 1 + 1 exchanges; lane l ends up with the total of value
+// 4 bit4(l) + 2 bit3(l) + bit2(l) (all four lanes of a quad hold it)
+__device__ __forceinline__ double transpose_sum8(double (&s)[8], int lane)
+{
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = b4 ? s[i] : s[i + 4], keep = b4 ? s[i + 4] : s[i];
+        s[i] = keep + shx(send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = b3 ? s[i] : s[i + 2], keep = b3 ? s[i + 2] : s[i];
+        s[i] = keep + shx(send, 8);
+    }
+    const double send = b2 ? s[0] : s[1], keep = b2 ? s[1] : s[0];
+    double r = keep + shx(send, 4);
+    r += shx(r, 2);
+    r += shx(r, 1);
+    return r;
+}
+
+// ---- distributed shared memory: remote stores that signal the receiver's mbarrier (no cluster-wide fences) --------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+// 8-byte store into the partner's shared memory; its completion is counted (8 bytes) on the partner's mbarrier
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Exchange protocol of one product q (both CTAs run it in step): thread 0 arms the local barrier xbar[q & 1] with the bytes
+// the partner will deliver, every thread computes its share and st.async-es it into the partner's buffer [q & 1], then waits
+// for the local barrier's phase (q >> 1) & 1. Buffers, barriers and the input vector xs are double-buffered by q & 1: the
+// partner delivers product q + 2 only after it has received this CTA's product q + 1, which this CTA sends after the CTA
+// barrier that follows all its reads of product q.
+struct Pair {
+    unsigned rank;      // this CTA's rank in the pair
+    const double *sc;   // [SR][N] shared-memory rows (own rows 0..SR-1)
+    double *xs;         // [2][N] product input (stage state / seed vector)
+    double *gb;         // [2][N] product results (row phase)
+    double *yp;         // [2][N] the partner's partial sums (column phase)
+    uint64_t *xbar;     // [2] exchange barriers
+    uint32_t gb_remote, yp_remote, xbar_remote; // shared::cluster addresses of the partner's gb, yp, xbar
+    uint32_t q;         // products done
+    __device__ __forceinline__ double *xin() const { return xs + (q & 1u) * N; }
+};
+
+// returns g_tid = r_tid + (A xin)_tid. P.xin() must be visible to all threads of this CTA (both CTAs hold the same vector).
+__device__ __forceinline__ double product_rows(Pair &P, const double *rr, const double (&creg)[CR], int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t pp = P.q & 1u, par = (P.q >> 1) & 1u;
+    if (tid == 0) mbar_expect_tx(&P.xbar[pp], HR * 8); // the partner's 128 rows
+    const double *xin = P.xin();
+    double xr[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double2 t = *reinterpret_cast<const double2 *>(xin + 64 * k + 2 * lane);
+        xr[2 * k] = t.x;
+        xr[2 * k + 1] = t.y;
+    }
+    double *mine = P.gb + pp * N;
+    const int sub = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    double s[8];
+    // register rows: warp w holds own rows SR + 8 w + r, lane l their columns {64k + 2l, 64k + 2l + 1}
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fma(creg[r * 8 + k], xr[k], acc);
+        s[r] = acc;
+    }
+    const double sum_reg = transpose_sum8(s, lane);
+    // shared-memory rows: warp w takes own rows 8 w + r
+    const double *rowp = P.sc + (size_t)(8 * warp) * N + 2 * lane;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2 t = *reinterpret_cast<const double2 *>(rowp + r * N + 64 * k);
+            acc = fma(t.x, xr[2 * k], acc);
+            acc = fma(t.y, xr[2 * k + 1], acc);
+        }
+        s[r] = acc;
+    }
+    const double sum_sm = transpose_sum8(s, lane);
+    if ((lane & 3) == 0) {
+        const int row_reg = (int)P.rank * HR + SR + 8 * warp + sub, row_sm = (int)P.rank * HR + 8 * warp + sub;
+        const double g_reg = rr[row_reg] + sum_reg, g_sm = rr[row_sm] + sum_sm;
+        mine[row_reg] = g_reg;
+        mine[row_sm] = g_sm;
+        const uint32_t rb = P.xbar_remote + pp * 8u;
+        st_async_f64(P.gb_remote + (pp * N + row_reg) * 8u, g_reg, rb);
+        st_async_f64(P.gb_remote + (pp * N + row_sm) * 8u, g_sm, rb);
+    }
+    __syncthreads();                // the own half is visible to the CTA
+    mbar_wait_or_trap(&P.xbar[pp], par);    // the partner's half has landed
+    const double g = mine[tid];
+    ++P.q;
+    return g;
+}
+
+// returns (A^T v)_tid for v = P.xin(), visible to all threads of this CTA. Register rows in column layout:
+// creg[i] = A[own row SR + i][tid].
+__device__ __forceinline__ double product_cols(Pair &P, const double (&creg)[CR], int tid)
+{
+    const uint32_t pp = P.q & 1u, par = (P.q >> 1) & 1u;
+    if (tid == 0) mbar_expect_tx(&P.xbar[pp], N * 8); // the partner's partial sums for all columns
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *vo = P.xin() + (int)P.rank * HR; // v of the own rows
+#pragma unroll
+    for (int i = 0; i < CR; i += 2) {
+        const double2 t = *reinterpret_cast<const double2 *>(vo + SR + i);
+        acc[i & 3] = fma(creg[i], t.x, acc[i & 3]);
+        acc[(i + 1) & 3] = fma(creg[i + 1], t.y, acc[(i + 1) & 3]);
+    }
+    const double *col = P.sc + tid;
+#pragma unroll 16
+    for (int i = 0; i < SR; i += 2) {
+        const double2 t = *reinterpret_cast<const double2 *>(vo + i);
+        acc[i & 3] = fma(col[(size_t)i * N], t.x, acc[i & 3]);
+        acc[(i + 1) & 3] = fma(col[(size_t)(i + 1) * N], t.y, acc[(i + 1) & 3]);
+    }
+    const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    st_async_f64(P.yp_remote + (pp * N + tid) * 8u, part, P.xbar_remote + pp * 8u);
+    mbar_wait_or_trap(&P.xbar[pp], par);
+    const double other = P.yp[pp * N + tid];
+    ++P.q;
+    return part + other; // IEEE addition is commutative: both CTAs get the same bits
+}
+
+template <class Tab, bool ADAPTIVE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGlvWideArgs a)
+{
+    constexpr int S = Tab::S, SADJ = Tab::SADJ;
+    constexpr int SE = Tab::FSAL ? S - 1 : S;
+    constexpr int BLK = 8 + 3 * SADJ * N; // [header | X_0.. | g_0.. | v_0..]
+    constexpr int OFF_X = 8, OFF_G = 8 + SADJ * N, OFF_V = 8 + 2 * SADJ * N;
+    static_assert(SADJ <= SADJ_MAX, "staging buffers");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sc = reinterpret_cast<double *>(smem_raw); // [SR][N]
+    double *xs = sc + (size_t)SR * N;                   // [2][N] stage state / seed vector handed to a product
+    double *gb = xs + 2 * N;                            // [2][N]
+    double *yp = gb + 2 * N;                            // [2][N]
+    double *rr = yp + 2 * N;                            // growth rates r
+    double *Vs = rr + N;                                // [SADJ][N]     phase 3 operands
+    double *Xs = Vs + SADJ_MAX * N;                     // [SADJ][PCOLS]
+    double *red = Xs + SADJ_MAX * PCOLS;                // [8] error-norm partials
+    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8); // [0]: matrix rows landed (TMA); [1], [2]: exchange barriers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int npar = N * N + N;
+
+    Pair P;
+    P.rank = cg::this_cluster().block_rank();
+    P.sc = sc;
+    P.xs = xs;
+    P.gb = gb;
+    P.yp = yp;
+    P.xbar = bar + 1;
+    P.gb_remote = mapa_u32(smem_u32(gb), P.rank ^ 1u);
+    P.yp_remote = mapa_u32(smem_u32(yp), P.rank ^ 1u);
+    P.xbar_remote = mapa_u32(smem_u32(bar + 1), P.rank ^ 1u);
+    P.q = 0;
+    const unsigned rank = P.rank;
+    const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    uint32_t bar_parity = 0;
+    const uint64_t pol = policy_evict_first(); // the matrix is read once per sweep: do not let it displace the slabs in L2
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_init(bar + 2, 1);
+        mbar_init_fence();
+    }
+    cluster_barrier(); // barriers initialised; the partner has started (its shared memory may be written from here on)
+    double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
+    double creg[CR];
+    bool row_init = false; // summed mode: this pair's partial-sum row has been written
+
+    for (int64_t b = pair_id; b < a.B; b += n_pairs) {
+        const double *pb = a.params + b * npar;
+        const double *Aown = pb + N + (size_t)rank * HR * N; // own rows; [0, SR) -> shared memory, [SR, HR) -> registers
+        const double *Ac = Aown + (size_t)SR * N;
+        // ------------------------------------------ forward sweep ------------------------------------------------------
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(SR * N * 8));
+#pragma unroll 1
+            for (uint32_t off = 0; off < (uint32_t)(SR * N * 8); off += TMA_PIECE)
+                bulk_g2s(reinterpret_cast<unsigned char *>(sc) + off, reinterpret_cast<const unsigned char *>(Aown) + off, TMA_PIECE, bar, pol);
+        }
+        // register rows, row layout: 8 rows per warp, 8 columns per lane and row
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
+                creg[r * 8 + 2 * k] = t.x;
+                creg[r * 8 + 2 * k + 1] = t.y;
+            }
+        rr[tid] = __ldg(pb + tid);
+        double x = a.x0[b * N + tid];
+        P.xin()[tid] = x;
+        mbar_wait_or_trap(bar, bar_parity);
+        bar_parity ^= 1u;
+        __syncthreads();
+        double t = a.ti, dt = a.dt0;
+        const double tf = a.tf;
+        int nck = 0, rejects = 0, status = 0, trials = 0;
+        double K[S];
+        double g0 = product_rows(P, rr, creg, tid);
+        K[0] = x * g0;
+        bool active = ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt);
+        bool fresh = true;
+        while (active) {
+            double *blk = slab + (int64_t)nck * BLK;
+            if (fresh) {
+                if (nck >= a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
+                blk[OFF_X + tid] = x;
+                blk[OFF_G + tid] = g0;
+                if (tid == 0) blk[0] = t;
+                if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
+                trials = 0;
+                fresh = false;
+            }
+#pragma unroll
+            for (int m = 1; m < SE; ++m) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < m; ++j)
+                    if (Tab::a(m, j) != 0.0) acc = fma(Tab::a(m, j), K[j], acc);
+                const double xm = fma(dt, acc, x);
+                P.xin()[tid] = xm;
+                if (m < SADJ) blk[OFF_X + m * N + tid] = xm;
+                __syncthreads();
+                const double gm = product_rows(P, rr, creg, tid);
+                K[m] = xm * gm;
+                if (m < SADJ) blk[OFF_G + m * N + tid] = gm;
+            }
+            double xnew;
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < SE; ++j)
+                    if (Tab::b(j) != 0.0) acc = fma(Tab::b(j), K[j], acc);
+                xnew = fma(dt, acc, x);
+            }
+            double gnew = 0.0;
+            if (Tab::FSAL) {
+                P.xin()[tid] = xnew;
+                __syncthreads();
+                gnew = product_rows(P, rr, creg, tid);
+                K[S - 1] = xnew * gnew;
+            }
+            bool accept = true;
+            double err = 0.0;
+            if (ADAPTIVE) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    if (Tab::db(j) != 0.0) acc = fma(Tab::db(j), K[j], acc);
+                double e = fabs(dt * acc) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, d));
+                __syncthreads(); // previous readers of red are done
+                if (lane == 0) red[warp] = e;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < NT / 32; ++w) err = fmax(err, red[w]);
+                accept = !(err > 1.0);
+            }
+            if (!accept) {
+                dt *= fmax(0.9 * inv_root<(Tab::ERROR_ORDER > 1 ? Tab::ERROR_ORDER - 1 : 1)>(err), 0.2);
+                ++rejects;
+                if (++trials >= 500) { status |= VA_TRAJ_NO_PROGRESS; break; }
+            } else {
+                x = xnew;
+                ++nck;
+                if (ADAPTIVE) {
+                    t += dt;
+                    if (err < 0.5) {
+                        constexpr int PO = Tab::STEPPER_ORDER;
+                        double floor_ = 1.0;
+#pragma unroll
+                        for (int k = 0; k < PO; ++k) floor_ *= 0.2;
+                        dt *= (err <= floor_) ? 4.5 : 9.0 / 10.0 * inv_root<PO>(err);
+                    }
+                    active = va_less_with_sign(t, tf, dt);
+                } else {
+                    t = a.ti + (double)nck * dt;
+                    active = va_less_eq_with_sign(t + dt, tf, dt);
+                }
+                fresh = true;
+                if (Tab::FSAL) {
+                    g0 = gnew;
+                    K[0] = K[S - 1];
+                } else if (active) {
+                    P.xin()[tid] = x;
+                    __syncthreads();
+                    g0 = product_rows(P, rr, creg, tid);
+                    K[0] = x * g0;
+                }
+            }
+        }
+        const int T = nck;
+        if (tid == 0) slab[(int64_t)T * BLK] = t;
+        if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
+        status = __syncthreads_or(status); // also: every slab store of the forward sweep is visible to the CTA
+        const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
+        if (rank == 0) {
+            a.x_final[b * N + tid] = failed ? nan("") : x;
+            if (tid == 0) {
+                if (a.n_accept) a.n_accept[b] = T;
+                if (a.n_reject) a.n_reject[b] = rejects;
+                if (a.status) a.status[b] = status;
+            }
+        }
+        const double t_final = t;
+
+        // ------------------------------------------ reverse sweep ------------------------------------------------------
+        for (int o = 0; o < a.n_out; ++o) {
+            double *lam_io = a.lambda + (b * a.n_out + o) * N;
+            const bool sum_mode = a.reduce == VA_REDUCE_SUM;
+            double *gbar = sum_mode ? a.partial + pair_id * npar : a.mu + (b * a.n_out + o) * npar;
+            const bool overwrite = !sum_mode || !row_init; // first use of this accumulator row
+            if (failed) {
+                if (rank == 0) {
+                    lam_io[tid] = nan("");
+                    if (!sum_mode)
+                        for (int k = tid; k < npar; k += NT) gbar[k] = nan("");
+                }
+                continue;
+            }
+            // ---- phase 2: state adjoint ----
+#pragma unroll
+            for (int i = 0; i < CR; ++i) creg[i] = __ldg(Ac + (size_t)i * N + tid); // column layout
+            double lam = a.objective == VA_OBJ_SUM ? 1.0 : a.objective == VA_OBJ_HALF_NORM2 ? x : lam_io[tid];
+            double rbar = 0.0;
+            double t_hi = t_final;
+#pragma unroll 1
+            for (int step = T - 1; step >= 0; --step) {
+                double *blk = slab + (int64_t)step * BLK;
+                const double t_lo = blk[0];
+                const double dt_s = t_hi - t_lo;
+                t_hi = t_lo;
+                double Xr[SADJ], Gr[SADJ], W[SADJ + 1];
+#pragma unroll
+                for (int m = 0; m < SADJ; ++m) {
+                    Xr[m] = blk[OFF_X + m * N + tid];
+                    Gr[m] = blk[OFF_G + m * N + tid];
+                }
+                W[0] = lam;
+#pragma unroll
+                for (int m = 1; m <= SADJ; ++m) W[m] = (Tab::b(m - 1) * dt_s) * lam;
+#pragma unroll
+                for (int m = SADJ; m >= 1; --m) {
+                    const double v = W[m] * Xr[m - 1];
+                    P.xin()[tid] = v;
+                    blk[OFF_V + (m - 1) * N + tid] = v;
+                    rbar += v;
+                    __syncthreads();
+                    const double atv = product_cols(P, creg, tid);
+                    const double gx = fma(W[m], Gr[m - 1], atv);
+                    W[0] += gx;
+#pragma unroll
+                    for (int k = 1; k < m; ++k)
+                        if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gx * Tab::a(m - 1, k - 1), dt_s, W[k]);
+                }
+                lam = W[0];
+            }
+            if (rank == 0) {
+                lam_io[tid] = lam;
+                if (overwrite) gbar[tid] = rbar;
+                else gbar[tid] += rbar;
+            }
+            __syncthreads(); // every v block of this CTA's slab is written
+
+            // ---- phase 3: Abar = sum_k v_k X_k^T; this CTA takes columns [128 rank, 128 rank + 128) in two 64-column passes ----
+            // thread (ty, tx): rows 8 ty + r, columns cb + 16 c + 2 tx + e  (r < 8, c < 4, e < 2)
+            const int ty = tid >> 3, tx = tid & 7;
+#pragma unroll 1
+            for (int cb = (int)rank * HR; cb < (int)rank * HR + HR; cb += PCOLS) {
+                double acc[8][8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+                double vreg[SADJ], xreg[SADJ];
+#pragma unroll
+                for (int m = 0; m < SADJ; ++m) { vreg[m] = 0.0; xreg[m] = 0.0; }
+                if (T > 0) {
+#pragma unroll
+                    for (int m = 0; m < SADJ; ++m) {
+                        vreg[m] = slab[OFF_V + m * N + tid];
+                        if (tid < PCOLS) xreg[m] = slab[OFF_X + m * N + cb + tid];
+                    }
+                }
+#pragma unroll 1
+                for (int step = 0; step < T; ++step) {
+                    __syncthreads(); // the previous step's operands have been consumed
+#pragma unroll
+                    for (int m = 0; m < SADJ; ++m) {
+                        Vs[m * N + tid] = vreg[m];
+                        if (tid < PCOLS) Xs[m * PCOLS + tid] = xreg[m];
+                    }
+                    __syncthreads();
+                    if (step + 1 < T) {
+                        const double *nb = slab + (int64_t)(step + 1) * BLK;
+#pragma unroll
+                        for (int m = 0; m < SADJ; ++m) {
+                            vreg[m] = nb[OFF_V + m * N + tid];
+                            if (tid < PCOLS) xreg[m] = nb[OFF_X + m * N + cb + tid];
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < SADJ; ++m) {
+                        double v8[8], x8[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 tv = *reinterpret_cast<const double2 *>(Vs + m * N + 8 * ty + 2 * q);
+                            v8[2 * q] = tv.x;
+                            v8[2 * q + 1] = tv.y;
+                            const double2 tx2 = *reinterpret_cast<const double2 *>(Xs + m * PCOLS + 16 * q + 2 * tx);
+                            x8[2 * q] = tx2.x;
+                            x8[2 * q + 1] = tx2.y;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) acc[r][c] = fma(v8[r], x8[c], acc[r][c]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        double2 *dst = reinterpret_cast<double2 *>(gbar + N + (size_t)(8 * ty + r) * N + cb + 16 * q + 2 * tx);
+                        double2 o2 = make_double2(acc[r][2 * q], acc[r][2 * q + 1]);
+                        if (!overwrite) {
+                            const double2 old = *dst;
+                            o2.x += old.x;
+                            o2.y += old.y;
+                        }
+                        *dst = o2;
+                    }
+                __syncthreads(); // staging buffers are free again
+            }
+            row_init = true;
+        }
+        __syncthreads(); // every reader of the shared-memory rows is done before the next matrix lands
+    }
+    if (a.reduce == VA_REDUCE_SUM && a.n_out > 0 && !row_init && rank == 0)
+        for (int k = tid; k < npar; k += NT) a.partial[pair_id * npar + k] = 0.0; // every trajectory of this pair failed
+    cluster_barrier(); // neither CTA leaves while the other could still address its shared memory
+}
+
+template <class Tab, bool ADAPTIVE>
+cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_glv_pair<Tab, ADAPTIVE><<<a.grid, NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+size_t va_glv_pair_smem()
+{
+    return (size_t)SR * N * 8 + (size_t)(7 * N + SADJ_MAX * N + SADJ_MAX * PCOLS + 8) * 8 + 64;
+}
+
+bool va_glv_pair_supported(int n, int stepper, int adaptive)
+{
+    if (n != N) return false;
+    if (stepper == VA_RK_RK4) return !adaptive;
+    if (stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5) return adaptive != 0;
+    return false;
+}
+
+int va_glv_pair_block_doubles(int stepper)
+{
+    const int sadj = stepper == VA_RK_RK4 ? TabRK4::SADJ : stepper == VA_RK_CK54 ? TabCK54::SADJ : TabDOPRI5::SADJ;
+    return 8 + 3 * sadj * N;
+}
+
+// a.grid must be even: CTAs 2p and 2p+1 form pair p (cluster dimensions 2 x 1 x 1); slab 2p / 2p+1, partial-sum row p
+cudaError_t va_glv_pair_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
+{
+    if (a.B <= 0) return cudaSuccess;
+    if (a.grid & 1) return cudaErrorInvalidValue;
+    const size_t smem = va_glv_pair_smem();
+    switch (a.stepper) {
+    case VA_RK_RK4: return launch<TabRK4, false>(a, st, smem);
+    case VA_RK_CK54: return launch<TabCK54, true>(a, st, smem);
+    case VA_RK_DOPRI5: return launch<TabDOPRI5, true>(a, st, smem);
+    }
+    return cudaErrorInvalidValue;
+}

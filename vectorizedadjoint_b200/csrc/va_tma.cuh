@@ -38,6 +38,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// bounded wait: a protocol error (bytes that never arrive) aborts the kernel with a trap instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, uint32_t parity)
+{
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
 __device__ __forceinline__ uint64_t policy_evict_last()
 {
     uint64_t p;
