@@ -39,6 +39,8 @@ constexpr int SR = 64;         // ... of which in shared memory (own rows [0, SR
 constexpr int CR = HR - SR;    // ... and in registers (own rows [SR, HR))
 constexpr int PCOLS = 64;      // columns of Abar per accumulation pass
 constexpr int SADJ_MAX = 6;
+constexpr int P3_STAGES = 4;   // phase 3: step blocks (v and X operands) in flight
+constexpr int P3_STAGE_DOUBLES = SADJ_MAX * (N + PCOLS);
 constexpr uint32_t TMA_PIECE = 32768;
 static_assert(N == NT && CR == 64 && SR % 8 == 0 && (SR * N * 8) % TMA_PIECE == 0, "geometry");
 
@@ -121,25 +123,36 @@ __device__ __forceinline__ double product_rows(Pair &P, const double *rr, const 
     double s[8];
     // register rows: warp w holds own rows SR + 8 w + r, lane l their columns {64k + 2l, 64k + 2l + 1}
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        double acc = 0.0;
+    for (int r = 0; r < 8; ++r) { // two chains per row
+        double acc0 = creg[r * 8] * xr[0], acc1 = creg[r * 8 + 4] * xr[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc = fma(creg[r * 8 + k], xr[k], acc);
-        s[r] = acc;
+        for (int k = 1; k < 4; ++k) {
+            acc0 = fma(creg[r * 8 + k], xr[k], acc0);
+            acc1 = fma(creg[r * 8 + 4 + k], xr[4 + k], acc1);
+        }
+        s[r] = acc0 + acc1;
     }
     const double sum_reg = transpose_sum8(s, lane);
     // shared-memory rows: warp w takes own rows 8 w + r
     const double *rowp = P.sc + (size_t)(8 * warp) * N + 2 * lane;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        double acc = 0.0;
+    for (int r0 = 0; r0 < 8; r0 += 4) { // four rows (16 LDS.128) in flight, two chains per row
+        double2 t[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double2 t = *reinterpret_cast<const double2 *>(rowp + r * N + 64 * k);
-            acc = fma(t.x, xr[2 * k], acc);
-            acc = fma(t.y, xr[2 * k + 1], acc);
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[r][k] = *reinterpret_cast<const double2 *>(rowp + (r0 + r) * N + 64 * k);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double acc0 = t[r][0].x * xr[0], acc1 = t[r][2].x * xr[4];
+            acc0 = fma(t[r][0].y, xr[1], acc0);
+            acc1 = fma(t[r][2].y, xr[5], acc1);
+            acc0 = fma(t[r][1].x, xr[2], acc0);
+            acc1 = fma(t[r][3].x, xr[6], acc1);
+            acc0 = fma(t[r][1].y, xr[3], acc0);
+            acc1 = fma(t[r][3].y, xr[7], acc1);
+            s[r0 + r] = acc0 + acc1;
         }
-        s[r] = acc;
     }
     const double sum_sm = transpose_sum8(s, lane);
     if ((lane & 3) == 0) {
@@ -164,22 +177,22 @@ __device__ __forceinline__ double product_cols(Pair &P, const double (&creg)[CR]
 {
     const uint32_t pp = P.q & 1u, par = (P.q >> 1) & 1u;
     if (tid == 0) mbar_expect_tx(&P.xbar[pp], N * 8); // the partner's partial sums for all columns
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const double *vo = P.xin() + (int)P.rank * HR; // v of the own rows
+    const double *col = P.sc + tid;
+#pragma unroll
+    for (int i = 0; i < SR; i += 2) { // shared-memory rows first: their loads overlap the register rows' arithmetic
+        const double2 t = *reinterpret_cast<const double2 *>(vo + i);
+        acc[i & 7] = fma(col[(size_t)i * N], t.x, acc[i & 7]);
+        acc[(i + 1) & 7] = fma(col[(size_t)(i + 1) * N], t.y, acc[(i + 1) & 7]);
+    }
 #pragma unroll
     for (int i = 0; i < CR; i += 2) {
         const double2 t = *reinterpret_cast<const double2 *>(vo + SR + i);
-        acc[i & 3] = fma(creg[i], t.x, acc[i & 3]);
-        acc[(i + 1) & 3] = fma(creg[i + 1], t.y, acc[(i + 1) & 3]);
+        acc[i & 7] = fma(creg[i], t.x, acc[i & 7]);
+        acc[(i + 1) & 7] = fma(creg[i + 1], t.y, acc[(i + 1) & 7]);
     }
-    const double *col = P.sc + tid;
-#pragma unroll 16
-    for (int i = 0; i < SR; i += 2) {
-        const double2 t = *reinterpret_cast<const double2 *>(vo + i);
-        acc[i & 3] = fma(col[(size_t)i * N], t.x, acc[i & 3]);
-        acc[(i + 1) & 3] = fma(col[(size_t)(i + 1) * N], t.y, acc[(i + 1) & 3]);
-    }
-    const double part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const double part = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     st_async_f64(P.yp_remote + (pp * N + tid) * 8u, part, P.xbar_remote + pp * 8u);
     mbar_wait_or_trap(&P.xbar[pp], par);
     const double other = P.yp[pp * N + tid];
@@ -201,10 +214,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
     double *gb = xs + 2 * N;                            // [2][N]
     double *yp = gb + 2 * N;                            // [2][N]
     double *rr = yp + 2 * N;                            // growth rates r
-    double *Vs = rr + N;                                // [SADJ][N]     phase 3 operands
-    double *Xs = Vs + SADJ_MAX * N;                     // [SADJ][PCOLS]
-    double *red = Xs + SADJ_MAX * PCOLS;                // [8] error-norm partials
-    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8); // [0]: matrix rows landed (TMA); [1], [2]: exchange barriers
+    double *p3buf = rr + N;                             // [P3_STAGES][SADJ x N of v | SADJ x PCOLS of X]  phase 3 operands
+    double *red = p3buf + P3_STAGES * P3_STAGE_DOUBLES; // [8] error-norm partials
+    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8); // [0]: matrix rows landed (TMA); [1], [2]: exchange; [3..]: phase 3 ring
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int npar = N * N + N;
 
@@ -222,11 +234,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
     const unsigned rank = P.rank;
     const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     uint32_t bar_parity = 0;
+    uint32_t p3q = 0; // phase 3 ring: step blocks consumed since kernel start (stage = p3q % P3_STAGES, parity = (p3q / P3_STAGES) & 1)
+    const uint64_t pol_slab = policy_evict_normal();
     const uint64_t pol = policy_evict_first(); // the matrix is read once per sweep: do not let it displace the slabs in L2
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
         mbar_init(bar + 2, 1);
+#pragma unroll 1
+        for (int k = 0; k < P3_STAGES; ++k) mbar_init(bar + 3 + k, 1);
         mbar_init_fence();
     }
     cluster_barrier(); // barriers initialised; the partner has started (its shared memory may be written from here on)
@@ -427,13 +443,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
             if (rank == 0) {
                 lam_io[tid] = lam;
                 if (overwrite) gbar[tid] = rbar;
-                else gbar[tid] += rbar;
+                else atomicAdd(gbar + tid, rbar);
             }
-            __syncthreads(); // every v block of this CTA's slab is written
+            // every v block of this CTA's slab is written (generic proxy); the bulk copies below read them through the async proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
 
             // ---- phase 3: Abar = sum_k v_k X_k^T; this CTA takes columns [128 rank, 128 rank + 128) in two 64-column passes ----
-            // thread (ty, tx): rows 8 ty + r, columns cb + 16 c + 2 tx + e  (r < 8, c < 4, e < 2)
+            // thread (ty, tx): rows 8 ty + r, columns cb + 16 c + 2 tx + e  (r < 8, c < 4, e < 2). The operands of a step
+            // (v_0..v_{s-1}: 2 KB each, X_0..X_{s-1}: 512 B of the pass's columns each) are brought in by TMA bulk copies,
+            // P3_STAGES steps ahead.
             const int ty = tid >> 3, tx = tid & 7;
+            auto p3_issue = [&](int step, int cb, uint32_t qi) { // thread 0: request the operands of `step` into stage qi % P3_STAGES
+                const int st = (int)(qi % P3_STAGES);
+                double *dstV = p3buf + (size_t)st * P3_STAGE_DOUBLES, *dstX = dstV + SADJ * N;
+                const double *blk = slab + (int64_t)step * BLK;
+                mbar_expect_tx(bar + 3 + st, (uint32_t)(SADJ * (N + PCOLS) * 8));
+#pragma unroll 1
+                for (int m = 0; m < SADJ; ++m) {
+                    bulk_g2s(dstV + m * N, blk + OFF_V + m * N, N * 8, bar + 3 + st, pol_slab);
+                    bulk_g2s(dstX + m * PCOLS, blk + OFF_X + m * N + cb, PCOLS * 8, bar + 3 + st, pol_slab);
+                }
+            };
 #pragma unroll 1
             for (int cb = (int)rank * HR; cb < (int)rank * HR + HR; cb += PCOLS) {
                 double acc[8][8];
@@ -441,33 +472,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
-                double vreg[SADJ], xreg[SADJ];
-#pragma unroll
-                for (int m = 0; m < SADJ; ++m) { vreg[m] = 0.0; xreg[m] = 0.0; }
-                if (T > 0) {
-#pragma unroll
-                    for (int m = 0; m < SADJ; ++m) {
-                        vreg[m] = slab[OFF_V + m * N + tid];
-                        if (tid < PCOLS) xreg[m] = slab[OFF_X + m * N + cb + tid];
-                    }
+                if (tid == 0) {
+#pragma unroll 1
+                    for (int k = 0; k < P3_STAGES && k < T; ++k) p3_issue(k, cb, p3q + (uint32_t)k);
                 }
 #pragma unroll 1
                 for (int step = 0; step < T; ++step) {
-                    __syncthreads(); // the previous step's operands have been consumed
-#pragma unroll
-                    for (int m = 0; m < SADJ; ++m) {
-                        Vs[m * N + tid] = vreg[m];
-                        if (tid < PCOLS) Xs[m * PCOLS + tid] = xreg[m];
-                    }
-                    __syncthreads();
-                    if (step + 1 < T) {
-                        const double *nb = slab + (int64_t)(step + 1) * BLK;
-#pragma unroll
-                        for (int m = 0; m < SADJ; ++m) {
-                            vreg[m] = nb[OFF_V + m * N + tid];
-                            if (tid < PCOLS) xreg[m] = nb[OFF_X + m * N + cb + tid];
-                        }
-                    }
+                    const int st = (int)(p3q % P3_STAGES);
+                    mbar_wait_or_trap(bar + 3 + st, (p3q / P3_STAGES) & 1u);
+                    const double *Vs = p3buf + (size_t)st * P3_STAGE_DOUBLES, *Xs = Vs + SADJ * N;
 #pragma unroll
                     for (int m = 0; m < SADJ; ++m) {
                         double v8[8], x8[8];
@@ -485,21 +498,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
 #pragma unroll
                             for (int c = 0; c < 8; ++c) acc[r][c] = fma(v8[r], x8[c], acc[r][c]);
                     }
+                    __syncthreads(); // every thread is done with this stage
+                    if (tid == 0 && step + P3_STAGES < T) p3_issue(step + P3_STAGES, cb, p3q + (uint32_t)P3_STAGES);
+                    ++p3q;
                 }
+                // Abar tile out: plain stores on first use of the row, fire-and-forget reductions afterwards (one writer per
+                // address, program order: deterministic)
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        double2 *dst = reinterpret_cast<double2 *>(gbar + N + (size_t)(8 * ty + r) * N + cb + 16 * q + 2 * tx);
-                        double2 o2 = make_double2(acc[r][2 * q], acc[r][2 * q + 1]);
-                        if (!overwrite) {
-                            const double2 old = *dst;
-                            o2.x += old.x;
-                            o2.y += old.y;
+                        double *dst = gbar + N + (size_t)(8 * ty + r) * N + cb + 16 * q + 2 * tx;
+                        if (overwrite) {
+                            *reinterpret_cast<double2 *>(dst) = make_double2(acc[r][2 * q], acc[r][2 * q + 1]);
+                        } else {
+                            atomicAdd(dst, acc[r][2 * q]);
+                            atomicAdd(dst + 1, acc[r][2 * q + 1]);
                         }
-                        *dst = o2;
                     }
-                __syncthreads(); // staging buffers are free again
             }
             row_init = true;
         }
@@ -523,7 +539,7 @@ cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
 
 size_t va_glv_pair_smem()
 {
-    return (size_t)SR * N * 8 + (size_t)(7 * N + SADJ_MAX * N + SADJ_MAX * PCOLS + 8) * 8 + 64;
+    return (size_t)SR * N * 8 + (size_t)(7 * N + P3_STAGES * P3_STAGE_DOUBLES + 8) * 8 + (3 + P3_STAGES) * 8 + 64;
 }
 
 bool va_glv_pair_supported(int n, int stepper, int adaptive)
