@@ -41,6 +41,9 @@ WORKLOADS = {
               "GLV N=16 (Npar=272), 2^20 parameter sets, cash_karp54 controlled rtol=atol=1e-8, t=[0,10], full r and A gradient"),
     "glv256": (2, 256, 2, True, 1e-8, 0.0, 10.0, 1e-3, 0, 1, 6,
                "GLV N=256 (Npar=65792), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; cluster-pair kernel (va_glv_pair.cu: matrix on chip in two SMs; VA_GLV_NO_PAIR=1: ring-streamed kernel va_glv_ring.cu); default batch 8192"),
+    "glv256long": (2, 256, 2, True, 1e-12, 0.0, 1000.0, 1e-3, 512, 1, 6,
+                   "GLV N=256 long horizon: cash_karp54 controlled rtol=atol=1e-12, t=[0,1000] (about 250 accepted steps per trajectory; "
+                   "store-stages slabs of 148 x 513 x 36.9 KB = 2.8 GB live in HBM, not L2); cluster-pair kernel; default batch 2048"),
     "vdp": (1, 2, 3, True, 1e-8, 0.0, 0.5, 1e-3, 1024, 1, 7,
             "Van der Pol, mu swept over [1,1024), 2^20 parameter sets, dopri5 controlled rtol=atol=1e-8, t=[0,0.5], dt0=1e-3"),
     "harmonic": (0, 2, 1, False, 0.0, 0.0, 10.0, 0.01, 1024, 2, 4,
@@ -218,7 +221,7 @@ def side_workload(args):
     system, n, stepper, adaptive, tol, ti, tf, dt0, max_steps, objective, stages, desc = WORKLOADS[args.workload]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    B = args.batch if (args.workload != "glv256" or args.batch != 1 << 20) else 8192
+    B = args.batch if (not args.workload.startswith("glv256") or args.batch != 1 << 20) else (8192 if args.workload == "glv256" else 2048)
     npar = va.npar_of(system, n)
     red = va.REDUCE_SUM if args.reduce == "sum" else va.REDUCE_NONE
     f64 = dict(dtype=torch.float64, device=dev)

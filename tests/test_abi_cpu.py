@@ -61,3 +61,15 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "va_oracle.h" not in txt and "libva_ref" not in txt and "import oracle" not in txt, os.path.join(base, f)
+
+
+def test_torch_front_end_imports_and_fails_loudly_without_gpu():
+    """The PyTorch front-end is plumbing over the C-ABI: importable anywhere, but without a CUDA device it must refuse to
+    construct a solver (no CPU path)."""
+    import torch
+    import vectorizedadjoint_b200 as va
+    from vectorizedadjoint_b200 import torch_api
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(va.EngineError):
+        torch_api.OdeSolver(va.SYS_HARMONIC, 2, va.RK_RK4, False, ti=0.0, tf=1.0, dt0=0.01)

@@ -26,6 +26,7 @@ struct VaGlvWideArgs {
     int grid;
     int blk_doubles;      // va_glv_t8.cu: doubles per step block (the v section is separate when n_out > 1)
     int recompute;        // streamed family: 1 = keep only (t_n, x_n) and recompute the stages in the reverse sweep
+    int flags;            // ring kernel: bit 1 = evict_last policy on the matrix stream, bit 2 = no register-cached rows
     struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
@@ -48,7 +49,7 @@ int va_glv_stream_block_doubles(int n, int stepper, int recompute);
 cudaError_t va_glv_stream_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
 // ring-streamed GLV kernel for 256 species (va_glv_ring.cu): one 256-thread CTA per SM, matrix streamed through a TMA ring,
-// store-stages policy; a.recompute carries its flag word (bit 1: evict_last matrix stream, bit 2: no register-cached rows)
+// store-stages policy; a.flags: bit 1 = evict_last matrix stream, bit 2 = no register-cached rows
 bool va_glv_ring_supported(int n, int stepper, int adaptive);
 int va_glv_ring_block_doubles(int stepper);
 size_t va_glv_ring_smem();

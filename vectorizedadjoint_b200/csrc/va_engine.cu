@@ -233,7 +233,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
         else if (e->pairk) VA_CUDA(va_glv_pair_forward_adjoint(a, st));
         else if (e->ring) {
-            a.recompute = e->ring_flags;
+            a.flags = e->ring_flags;
             VA_CUDA(va_glv_ring_forward_adjoint(a, st));
         } else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
         ++e->launches;
@@ -606,9 +606,8 @@ int va_forward_batch(va_engine *e, const va_batch_args *a)
     VA_CUDA(cudaSetDevice(e->device));
     const int n = e->desc.n_state, npar = e->desc.n_par;
     const int64_t B = a->batch;
-    if (is_glv(e) && B > (int64_t)e->grid * e->tpc)
-        return fail(VA_E_UNSUPPORTED, "split forward/adjoint on the GLV path keeps checkpoints for at most one wave of CTAs; "
-                                      "use va_forward_adjoint_batch for larger batches");
+    // GLV path: the slabs keep the checkpoints of the first wave of trajectories only (va_get_checkpoints serves those);
+    // va_adjoint_batch does not need them, it re-integrates from the recorded inputs (deterministic, identical steps)
     if (int rc = e->se_x0.ensure((size_t)B * n * 8)) return rc;
     if (int rc = e->se_par.ensure((size_t)B * npar * 8)) return rc;
     if (int rc = e->se_xf.ensure((size_t)B * n * 8)) return rc;
@@ -711,6 +710,8 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     if (!e || !count) return fail(VA_E_INVALID, "null argument");
     if (e->se_B <= 0) return fail(VA_E_STATE, "no forward sweep recorded on this engine");
     if (b < 0 || b >= e->se_B) return fail(VA_E_INVALID, "trajectory index out of range");
+    if (is_glv(e) && b >= (e->pairk ? e->grid / 2 : (int64_t)e->grid * e->tpc))
+        return fail(VA_E_UNSUPPORTED, "the GLV path keeps the checkpoints of the first wave of trajectories only (one per resident slot)");
     const int n = e->desc.n_state;
     const int T = e->se_accept_host[(size_t)b];
     *count = T + 1;

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_ring(const __grid_constant__ VaGl
     R.parity = 0;
     R.cnext = 0;
     R.A = nullptr;
-    R.pol = (a.recompute & 2) ? policy_evict_last() : policy_evict_normal(); // bit 1 of the flag word: keep matrices in L2
+    R.pol = (a.flags & 2) ? policy_evict_last() : policy_evict_normal(); // keep the matrices of the resident CTAs in L2
     if (tid == 0) {
 #pragma unroll 1
         for (int s = 0; s < RING; ++s) mbar_init(&bars[s], 1);
@@ -522,7 +522,7 @@ cudaError_t launch2(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
 template <class Tab, bool ADAPTIVE>
 cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
 {
-    return (a.recompute & 4) ? launch2<Tab, ADAPTIVE, 0>(a, st, smem) : launch2<Tab, ADAPTIVE, 64>(a, st, smem);
+    return (a.flags & 4) ? launch2<Tab, ADAPTIVE, 0>(a, st, smem) : launch2<Tab, ADAPTIVE, 64>(a, st, smem);
 }
 
 } // namespace
@@ -543,8 +543,7 @@ int va_glv_ring_block_doubles(int stepper)
     return 8 + 3 * sadj * N;
 }
 
-// a.recompute carries the kernel's flag word here (the family is store-stages only): bit 1 = evict_last policy on the
-// matrix stream, bit 2 = no register-cached rows (CR = 0)
+// a.flags: bit 1 = evict_last policy on the matrix stream, bit 2 = no register-cached rows (CR = 0)
 cudaError_t va_glv_ring_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;
