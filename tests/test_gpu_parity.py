@@ -437,7 +437,7 @@ def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     np.testing.assert_array_equal(x[0], x0[3])
 
 
-@pytest.mark.parametrize("kernel", ["k_glv_pair", "k_glv_ring:2", "k_glv_ring:0", "k_glv_ring:6"])
+@pytest.mark.parametrize("kernel", ["k_glv_pair:2", "k_glv_pair:4", "k_glv_ring:2", "k_glv_ring:0", "k_glv_ring:6"])
 def test_glv256_onchip_and_ring_kernels_agree_with_streamed_kernel_and_oracle(va, monkeypatch, kernel):
     """256 species, store-stages policy. Three independent thread/data maps of the same algorithm:
     k_glv_pair (va_glv_pair.cu, default: two CTAs of a cluster hold the matrix on chip and exchange product halves through
@@ -453,6 +453,8 @@ def test_glv256_onchip_and_ring_kernels_agree_with_streamed_kernel_and_oracle(va
     if name == "k_glv_ring":
         monkeypatch.setenv("VA_GLV_NO_PAIR", "1")
         monkeypatch.setenv("VA_RING_FLAGS", flags)
+    else:
+        monkeypatch.setenv("VA_GLV_CLUSTER", flags)  # CTAs per trajectory: 2 (registers + shared memory) or 4 (registers only)
     res = []
     for fast in (True, False):
         if not fast:
@@ -491,13 +493,16 @@ def test_glv256_onchip_and_ring_kernels_agree_with_streamed_kernel_and_oracle(va
     assert_close(ha["mu"][:, 0], o["mu"], what="mu")
 
 
-@pytest.mark.parametrize("kernel", ["k_glv_pair", "k_glv_ring"])
+@pytest.mark.parametrize("kernel", ["k_glv_pair:2", "k_glv_pair:4", "k_glv_ring"])
 def test_glv256_many_waves_summed_mode(va, monkeypatch, kernel):
     """More trajectories than resident CTAs / CTA pairs (each integrates several trajectories and keeps adding to its
     partial-sum row): the summed gradient equals the sum of the per-trajectory gradients, and a replicated parameter set
     gives identical rows."""
+    kernel, _, cl = kernel.partition(":")
     if kernel == "k_glv_ring":
         monkeypatch.setenv("VA_GLV_NO_PAIR", "1")
+    else:
+        monkeypatch.setenv("VA_GLV_CLUSTER", cl)
     N, B = 256, 400
     base = oracle.synth_params(oracle.SYS_GLV, N, 99, 0, 3)
     p = base[np.arange(B) % 3]

@@ -26,6 +26,7 @@ struct VaGlvWideArgs {
     int grid;
     int blk_doubles;      // va_glv_t8.cu: doubles per step block (the v section is separate when n_out > 1)
     int recompute;        // streamed family: 1 = keep only (t_n, x_n) and recompute the stages in the reverse sweep
+    int cluster;          // cluster kernel (va_glv_pair.cu): CTAs per trajectory (2 or 4)
     int flags;            // ring kernel: bit 1 = evict_last policy on the matrix stream, bit 2 = no register-cached rows
     struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
 };
@@ -55,11 +56,12 @@ int va_glv_ring_block_doubles(int stepper);
 size_t va_glv_ring_smem();
 cudaError_t va_glv_ring_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
-// cluster-pair GLV kernel for 256 species (va_glv_pair.cu): two CTAs (a 2 x 1 x 1 cluster) per trajectory hold the matrix on
-// chip (registers + shared memory) and exchange product halves through distributed shared memory; a.grid must be even
+// cluster GLV kernel for 256 species (va_glv_pair.cu): a.cluster = 2 or 4 CTAs (one thread-block cluster) per trajectory hold
+// the matrix on chip (registers, + shared memory at 2) and exchange product parts through distributed shared memory; a.grid
+// must be a multiple of a.cluster
 bool va_glv_pair_supported(int n, int stepper, int adaptive);
 int va_glv_pair_block_doubles(int stepper);
-size_t va_glv_pair_smem();
+cudaError_t va_glv_pair_max_clusters(int stepper, int cluster, int sm_count, int *n);
 cudaError_t va_glv_pair_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
 // out[k] (+)= sum_{g<G} in[g*stride + k], deterministic order

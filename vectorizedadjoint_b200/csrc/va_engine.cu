@@ -83,7 +83,8 @@ struct va_engine {
     int glv_blk = 0;  // doubles per step block of the register-kernel slab
     bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
     int ring_flags = 0;
-    bool pairk = false; // FAM_GLV_STREAM served by va_glv_pair.cu (256 species, matrix on chip in a 2-CTA cluster)
+    bool pairk = false; // FAM_GLV_STREAM served by va_glv_pair.cu (256 species, matrix on chip in a cluster of pair_cl CTAs)
+    int pair_cl = 2;
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -216,7 +217,8 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.n_accept = acc; a.n_reject = rej; a.status = sta;
         a.slab = e->slab.as<double>(); a.slab_stride = e->slab_stride; a.partial = e->partial.as<double>();
         a.grid = (int)std::min<int64_t>(e->grid, (d.B + e->tpc - 1) / e->tpc);
-        if (e->pairk) a.grid = 2 * (int)std::min<int64_t>(e->grid / 2, d.B); // two CTAs per trajectory
+        if (e->pairk) a.grid = e->pair_cl * (int)std::min<int64_t>(e->grid / e->pair_cl, d.B); // pair_cl CTAs per trajectory
+        a.cluster = e->pair_cl;
         a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE;
         a.blk_doubles = e->glv_blk;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
@@ -238,7 +240,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         } else VA_CUDA(va_glv_stream_forward_adjoint(a, st));
         ++e->launches;
         if (native_sum) {
-            VA_CUDA(va_reduce_rows(e->partial.as<double>(), e->pairk ? a.grid / 2 : (int64_t)a.grid * e->tpc, npar, npar, d.mu,
+            VA_CUDA(va_reduce_rows(e->partial.as<double>(), e->pairk ? a.grid / e->pair_cl : (int64_t)a.grid * e->tpc, npar, npar, d.mu,
                                    d.mu_accumulate ? 1 : 0, st));
             ++e->launches;
         } else if (sum && !d.forward_only) {
@@ -489,7 +491,13 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
                   !getenv("VA_GLV_NO_RING");
         if (e->pairk) {
             e->ctas_per_sm = 1;
-            e->grid = e->sm_count / 2 * 2;
+            e->pair_cl = getenv("VA_GLV_CLUSTER") && atoi(getenv("VA_GLV_CLUSTER")) == 4 ? 4 : 2;
+            int nclusters = 0;
+            cudaError_t ce = va_glv_pair_max_clusters(desc->stepper, e->pair_cl, e->sm_count, &nclusters);
+            if (ce != cudaSuccess || nclusters < 1)
+                return bail(VA_E_CUDA, std::string("cluster occupancy query failed: ") + cudaGetErrorString(ce));
+            e->grid = e->pair_cl * std::min(nclusters, e->sm_count / e->pair_cl);
+            if (getenv("VA_DEBUG")) fprintf(stderr, "va: k_glv_pair: %d clusters of %d CTAs\n", e->grid / e->pair_cl, e->pair_cl);
             e->glv_blk = va_glv_pair_block_doubles(desc->stepper);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
         }
@@ -710,7 +718,7 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     if (!e || !count) return fail(VA_E_INVALID, "null argument");
     if (e->se_B <= 0) return fail(VA_E_STATE, "no forward sweep recorded on this engine");
     if (b < 0 || b >= e->se_B) return fail(VA_E_INVALID, "trajectory index out of range");
-    if (is_glv(e) && b >= (e->pairk ? e->grid / 2 : (int64_t)e->grid * e->tpc))
+    if (is_glv(e) && b >= (e->pairk ? e->grid / e->pair_cl : (int64_t)e->grid * e->tpc))
         return fail(VA_E_UNSUPPORTED, "the GLV path keeps the checkpoints of the first wave of trajectories only (one per resident slot)");
     const int n = e->desc.n_state;
     const int T = e->se_accept_host[(size_t)b];
@@ -733,7 +741,7 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
         // first wave: trajectory b = slot b, slab 0 (cluster-pair kernel: CTA 2b of pair b)
-        const double *base = e->slab.as<double>() + b * (e->pairk ? 2 : e->pair) * e->slab_stride;
+        const double *base = e->slab.as<double>() + b * (e->pairk ? e->pair_cl : e->pair) * e->slab_stride;
         const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE || e->ring || e->pairk ? e->glv_blk
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));

@@ -34,15 +34,14 @@ using namespace va_tma;
 
 constexpr int NT = 256;        // threads per CTA
 constexpr int N = 256;         // species: thread i owns component i
-constexpr int HR = N / 2;      // matrix rows per CTA
-constexpr int SR = 64;         // ... of which in shared memory (own rows [0, SR))
-constexpr int CR = HR - SR;    // ... and in registers (own rows [SR, HR))
+constexpr int CR = 64;         // matrix rows per CTA held in registers (own rows [SR, HR)), 128 registers per thread
+// CL = CTAs per cluster (2 or 4): HR = N / CL matrix rows per CTA, of which SR = HR - CR in shared memory (own rows [0, SR))
 constexpr int PCOLS = 64;      // columns of Abar per accumulation pass
 constexpr int SADJ_MAX = 6;
 constexpr int P3_STAGES = 4;   // phase 3: step blocks (v and X operands) in flight
 constexpr int P3_STAGE_DOUBLES = SADJ_MAX * (N + PCOLS);
 constexpr uint32_t TMA_PIECE = 32768;
-static_assert(N == NT && CR == 64 && SR % 8 == 0 && (SR * N * 8) % TMA_PIECE == 0, "geometry");
+static_assert(N == NT && CR == 64, "geometry");
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -92,24 +91,29 @@ __device__ __forceinline__ void cluster_barrier()
 // for the local barrier's phase (q >> 1) & 1. Buffers, barriers and the input vector xs are double-buffered by q & 1: the
 // partner delivers product q + 2 only after it has received this CTA's product q + 1, which this CTA sends after the CTA
 // barrier that follows all its reads of product q.
+template <int CL>
 struct Pair {
-    unsigned rank;      // this CTA's rank in the pair
+    static constexpr int HR = N / CL, SR = HR - CR;
+    static_assert((CL == 2 || CL == 4) && SR >= 0 && SR % 8 == 0 && (SR * N * 8) % TMA_PIECE == 0, "geometry");
+    unsigned rank;      // this CTA's rank in the cluster
     const double *sc;   // [SR][N] shared-memory rows (own rows 0..SR-1)
     double *xs;         // [2][N] product input (stage state / seed vector)
     double *gb;         // [2][N] product results (row phase)
-    double *yp;         // [2][N] the partner's partial sums (column phase)
+    double *yp;         // [2][CL][N] partial sums by source rank (column phase)
     uint64_t *xbar;     // [2] exchange barriers
-    uint32_t gb_remote, yp_remote, xbar_remote; // shared::cluster addresses of the partner's gb, yp, xbar
+    uint32_t gb_remote[CL - 1], yp_remote[CL - 1], xbar_remote[CL - 1]; // shared::cluster addresses of peer (rank + 1 + d) % CL's buffers
     uint32_t q;         // products done
     __device__ __forceinline__ double *xin() const { return xs + (q & 1u) * N; }
 };
 
-// returns g_tid = r_tid + (A xin)_tid. P.xin() must be visible to all threads of this CTA (both CTAs hold the same vector).
-__device__ __forceinline__ double product_rows(Pair &P, const double *rr, const double (&creg)[CR], int tid)
+// returns g_tid = r_tid + (A xin)_tid. P.xin() must be visible to all threads of this CTA (all CTAs hold the same vector).
+template <int CL>
+__device__ __forceinline__ double product_rows(Pair<CL> &P, const double *rr, const double (&creg)[CR], int tid)
 {
+    constexpr int HR = Pair<CL>::HR, SR = Pair<CL>::SR;
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t pp = P.q & 1u, par = (P.q >> 1) & 1u;
-    if (tid == 0) mbar_expect_tx(&P.xbar[pp], HR * 8); // the partner's 128 rows
+    if (tid == 0) mbar_expect_tx(&P.xbar[pp], (CL - 1) * HR * 8); // the peers' rows
     const double *xin = P.xin();
     double xr[8];
 #pragma unroll
@@ -133,39 +137,50 @@ __device__ __forceinline__ double product_rows(Pair &P, const double *rr, const 
         s[r] = acc0 + acc1;
     }
     const double sum_reg = transpose_sum8(s, lane);
-    // shared-memory rows: warp w takes own rows 8 w + r
-    const double *rowp = P.sc + (size_t)(8 * warp) * N + 2 * lane;
+    double sum_sm = 0.0;
+    if (SR > 0) {
+        // shared-memory rows: warp w takes own rows (SR / 8) w + r. (No store or asm statement between the two parts: the
+        // compiler hoists these loads above the register rows' arithmetic.)
+        constexpr int RW = SR / 8; // 8 at CL = 2
+        static_assert(SR == 0 || RW == 8, "shared-memory rows: 8 per warp");
+        const double *rowp = P.sc + (size_t)(8 * warp) * N + 2 * lane;
 #pragma unroll
-    for (int r0 = 0; r0 < 8; r0 += 4) { // four rows (16 LDS.128) in flight, two chains per row
-        double2 t[4][4];
+        for (int r0 = 0; r0 < 8; r0 += 4) { // four rows (16 LDS.128) in flight, two chains per row
+            double2 t[4][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) t[r][k] = *reinterpret_cast<const double2 *>(rowp + (r0 + r) * N + 64 * k);
+                for (int k = 0; k < 4; ++k) t[r][k] = *reinterpret_cast<const double2 *>(rowp + (r0 + r) * N + 64 * k);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            double acc0 = t[r][0].x * xr[0], acc1 = t[r][2].x * xr[4];
-            acc0 = fma(t[r][0].y, xr[1], acc0);
-            acc1 = fma(t[r][2].y, xr[5], acc1);
-            acc0 = fma(t[r][1].x, xr[2], acc0);
-            acc1 = fma(t[r][3].x, xr[6], acc1);
-            acc0 = fma(t[r][1].y, xr[3], acc0);
-            acc1 = fma(t[r][3].y, xr[7], acc1);
-            s[r0 + r] = acc0 + acc1;
+            for (int r = 0; r < 4; ++r) {
+                double acc0 = t[r][0].x * xr[0], acc1 = t[r][2].x * xr[4];
+                acc0 = fma(t[r][0].y, xr[1], acc0);
+                acc1 = fma(t[r][2].y, xr[5], acc1);
+                acc0 = fma(t[r][1].x, xr[2], acc0);
+                acc1 = fma(t[r][3].x, xr[6], acc1);
+                acc0 = fma(t[r][1].y, xr[3], acc0);
+                acc1 = fma(t[r][3].y, xr[7], acc1);
+                s[r0 + r] = acc0 + acc1;
+            }
+        }
+        sum_sm = transpose_sum8(s, lane);
+    }
+    if ((lane & 3) == 0) {
+        const int row_reg = (int)P.rank * HR + SR + 8 * warp + sub;
+        const double g_reg = rr[row_reg] + sum_reg;
+        mine[row_reg] = g_reg;
+#pragma unroll
+        for (int d = 0; d < CL - 1; ++d) st_async_f64(P.gb_remote[d] + (pp * N + row_reg) * 8u, g_reg, P.xbar_remote[d] + pp * 8u);
+        if (SR > 0) {
+            const int row_sm = (int)P.rank * HR + 8 * warp + sub;
+            const double g_sm = rr[row_sm] + sum_sm;
+            mine[row_sm] = g_sm;
+#pragma unroll
+            for (int d = 0; d < CL - 1; ++d) st_async_f64(P.gb_remote[d] + (pp * N + row_sm) * 8u, g_sm, P.xbar_remote[d] + pp * 8u);
         }
     }
-    const double sum_sm = transpose_sum8(s, lane);
-    if ((lane & 3) == 0) {
-        const int row_reg = (int)P.rank * HR + SR + 8 * warp + sub, row_sm = (int)P.rank * HR + 8 * warp + sub;
-        const double g_reg = rr[row_reg] + sum_reg, g_sm = rr[row_sm] + sum_sm;
-        mine[row_reg] = g_reg;
-        mine[row_sm] = g_sm;
-        const uint32_t rb = P.xbar_remote + pp * 8u;
-        st_async_f64(P.gb_remote + (pp * N + row_reg) * 8u, g_reg, rb);
-        st_async_f64(P.gb_remote + (pp * N + row_sm) * 8u, g_sm, rb);
-    }
-    __syncthreads();                // the own half is visible to the CTA
-    mbar_wait_or_trap(&P.xbar[pp], par);    // the partner's half has landed
+    __syncthreads();                      // the own rows are visible to the CTA
+    mbar_wait_or_trap(&P.xbar[pp], par);  // the peers' rows have landed
     const double g = mine[tid];
     ++P.q;
     return g;
@@ -173,18 +188,22 @@ __device__ __forceinline__ double product_rows(Pair &P, const double *rr, const 
 
 // returns (A^T v)_tid for v = P.xin(), visible to all threads of this CTA. Register rows in column layout:
 // creg[i] = A[own row SR + i][tid].
-__device__ __forceinline__ double product_cols(Pair &P, const double (&creg)[CR], int tid)
+template <int CL>
+__device__ __forceinline__ double product_cols(Pair<CL> &P, const double (&creg)[CR], int tid)
 {
+    constexpr int HR = Pair<CL>::HR, SR = Pair<CL>::SR;
     const uint32_t pp = P.q & 1u, par = (P.q >> 1) & 1u;
-    if (tid == 0) mbar_expect_tx(&P.xbar[pp], N * 8); // the partner's partial sums for all columns
+    if (tid == 0) mbar_expect_tx(&P.xbar[pp], (CL - 1) * N * 8); // the peers' partial sums for all columns
     double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const double *vo = P.xin() + (int)P.rank * HR; // v of the own rows
-    const double *col = P.sc + tid;
+    if (SR > 0) {
+        const double *col = P.sc + tid;
 #pragma unroll
-    for (int i = 0; i < SR; i += 2) { // shared-memory rows first: their loads overlap the register rows' arithmetic
-        const double2 t = *reinterpret_cast<const double2 *>(vo + i);
-        acc[i & 7] = fma(col[(size_t)i * N], t.x, acc[i & 7]);
-        acc[(i + 1) & 7] = fma(col[(size_t)(i + 1) * N], t.y, acc[(i + 1) & 7]);
+        for (int i = 0; i < SR; i += 2) { // shared-memory rows first: their loads overlap the register rows' arithmetic
+            const double2 t = *reinterpret_cast<const double2 *>(vo + i);
+            acc[i & 7] = fma(col[(size_t)i * N], t.x, acc[i & 7]);
+            acc[(i + 1) & 7] = fma(col[(size_t)(i + 1) * N], t.y, acc[(i + 1) & 7]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < CR; i += 2) {
@@ -193,16 +212,29 @@ __device__ __forceinline__ double product_cols(Pair &P, const double (&creg)[CR]
         acc[(i + 1) & 7] = fma(creg[i + 1], t.y, acc[(i + 1) & 7]);
     }
     const double part = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    st_async_f64(P.yp_remote + (pp * N + tid) * 8u, part, P.xbar_remote + pp * 8u);
+#pragma unroll
+    for (int d = 0; d < CL - 1; ++d) st_async_f64(P.yp_remote[d] + ((pp * CL + P.rank) * N + tid) * 8u, part, P.xbar_remote[d] + pp * 8u);
     mbar_wait_or_trap(&P.xbar[pp], par);
-    const double other = P.yp[pp * N + tid];
+    double y;
+    if (CL == 2) {
+        y = part + P.yp[(pp * CL + (P.rank ^ 1u)) * N + tid]; // IEEE addition is commutative: both CTAs get the same bits
+    } else {
+        // sum in rank order, the own partial sum in its place: every CTA of the cluster gets the same bits
+        y = 0.0;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {
+            const double term = (unsigned)r == P.rank ? part : P.yp[(pp * CL + r) * N + tid];
+            y = r == 0 ? term : y + term;
+        }
+    }
     ++P.q;
-    return part + other; // IEEE addition is commutative: both CTAs get the same bits
+    return y;
 }
 
-template <class Tab, bool ADAPTIVE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGlvWideArgs a)
+template <class Tab, bool ADAPTIVE, int CL>
+__global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGlvWideArgs a)
 {
+    constexpr int HR = Pair<CL>::HR, SR = Pair<CL>::SR;
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S;
     constexpr int BLK = 8 + 3 * SADJ * N; // [header | X_0.. | g_0.. | v_0..]
@@ -212,27 +244,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
     double *sc = reinterpret_cast<double *>(smem_raw); // [SR][N]
     double *xs = sc + (size_t)SR * N;                   // [2][N] stage state / seed vector handed to a product
     double *gb = xs + 2 * N;                            // [2][N]
-    double *yp = gb + 2 * N;                            // [2][N]
-    double *rr = yp + 2 * N;                            // growth rates r
+    double *yp = gb + 2 * N;                            // [2][CL][N]
+    double *rr = yp + 2 * CL * N;                       // growth rates r
     double *p3buf = rr + N;                             // [P3_STAGES][SADJ x N of v | SADJ x PCOLS of X]  phase 3 operands
     double *red = p3buf + P3_STAGES * P3_STAGE_DOUBLES; // [8] error-norm partials
     uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8); // [0]: matrix rows landed (TMA); [1], [2]: exchange; [3..]: phase 3 ring
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int npar = N * N + N;
 
-    Pair P;
+    Pair<CL> P;
     P.rank = cg::this_cluster().block_rank();
     P.sc = sc;
     P.xs = xs;
     P.gb = gb;
     P.yp = yp;
     P.xbar = bar + 1;
-    P.gb_remote = mapa_u32(smem_u32(gb), P.rank ^ 1u);
-    P.yp_remote = mapa_u32(smem_u32(yp), P.rank ^ 1u);
-    P.xbar_remote = mapa_u32(smem_u32(bar + 1), P.rank ^ 1u);
+#pragma unroll
+    for (int d = 0; d < CL - 1; ++d) {
+        const uint32_t peer = (P.rank + 1u + (uint32_t)d) % CL;
+        P.gb_remote[d] = mapa_u32(smem_u32(gb), peer);
+        P.yp_remote[d] = mapa_u32(smem_u32(yp), peer);
+        P.xbar_remote[d] = mapa_u32(smem_u32(bar + 1), peer);
+    }
     P.q = 0;
     const unsigned rank = P.rank;
-    const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int64_t pair_id = blockIdx.x / CL, n_pairs = gridDim.x / CL;
     uint32_t bar_parity = 0;
     uint32_t p3q = 0; // phase 3 ring: step blocks consumed since kernel start (stage = p3q % P3_STAGES, parity = (p3q / P3_STAGES) & 1)
     const uint64_t pol_slab = policy_evict_normal();
@@ -255,7 +291,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
         const double *Aown = pb + N + (size_t)rank * HR * N; // own rows; [0, SR) -> shared memory, [SR, HR) -> registers
         const double *Ac = Aown + (size_t)SR * N;
         // ------------------------------------------ forward sweep ------------------------------------------------------
-        if (tid == 0) {
+        if (SR > 0 && tid == 0) {
             mbar_expect_tx(bar, (uint32_t)(SR * N * 8));
 #pragma unroll 1
             for (uint32_t off = 0; off < (uint32_t)(SR * N * 8); off += TMA_PIECE)
@@ -273,8 +309,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
         rr[tid] = __ldg(pb + tid);
         double x = a.x0[b * N + tid];
         P.xin()[tid] = x;
-        mbar_wait_or_trap(bar, bar_parity);
-        bar_parity ^= 1u;
+        if (SR > 0) {
+            mbar_wait_or_trap(bar, bar_parity);
+            bar_parity ^= 1u;
+        }
         __syncthreads();
         double t = a.ti, dt = a.dt0;
         const double tf = a.tf;
@@ -526,21 +564,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) k_glv_pair(co
     cluster_barrier(); // neither CTA leaves while the other could still address its shared memory
 }
 
-template <class Tab, bool ADAPTIVE>
-cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
+template <class Tab, bool ADAPTIVE, int CL>
+size_t smem_bytes()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return (size_t)Pair<CL>::SR * N * 8 + (size_t)((5 + 2 * CL) * N + P3_STAGES * P3_STAGE_DOUBLES + 8) * 8 + (3 + P3_STAGES) * 8 + 64;
+}
+
+// launch configuration with the cluster dimension attribute (the kernel carries no compile-time cluster size)
+template <class Tab, bool ADAPTIVE, int CL>
+cudaError_t configure(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &at, int grid, cudaStream_t st)
+{
+    const size_t smem = smem_bytes<Tab, ADAPTIVE, CL>();
+    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_glv_pair<Tab, ADAPTIVE><<<a.grid, NT, smem, st>>>(a);
-    return cudaGetLastError();
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CL;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return cudaSuccess;
+}
+template <class Tab, bool ADAPTIVE, int CL>
+cudaError_t launch2(const VaGlvWideArgs &a, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    cudaError_t e = configure<Tab, ADAPTIVE, CL>(cfg, at, a.grid, st);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL>, a);
+}
+template <class Tab, bool ADAPTIVE>
+cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st)
+{
+    return a.cluster == 4 ? launch2<Tab, ADAPTIVE, 4>(a, st) : launch2<Tab, ADAPTIVE, 2>(a, st);
+}
+template <class Tab, bool ADAPTIVE, int CL>
+cudaError_t max_clusters2(int sm_count, int *n)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    cudaError_t e = configure<Tab, ADAPTIVE, CL>(cfg, at, sm_count / CL * CL, nullptr);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveClusters(n, k_glv_pair<Tab, ADAPTIVE, CL>, &cfg);
+}
+template <class Tab, bool ADAPTIVE>
+cudaError_t max_clusters(int cl, int sm_count, int *n)
+{
+    return cl == 4 ? max_clusters2<Tab, ADAPTIVE, 4>(sm_count, n) : max_clusters2<Tab, ADAPTIVE, 2>(sm_count, n);
 }
 
 } // namespace
-
-size_t va_glv_pair_smem()
-{
-    return (size_t)SR * N * 8 + (size_t)(7 * N + P3_STAGES * P3_STAGE_DOUBLES + 8) * 8 + (3 + P3_STAGES) * 8 + 64;
-}
 
 bool va_glv_pair_supported(int n, int stepper, int adaptive)
 {
@@ -556,16 +635,27 @@ int va_glv_pair_block_doubles(int stepper)
     return 8 + 3 * sadj * N;
 }
 
-// a.grid must be even: CTAs 2p and 2p+1 form pair p (cluster dimensions 2 x 1 x 1); slab 2p / 2p+1, partial-sum row p
+// co-resident clusters of `cluster` CTAs the device can hold (the persistent grid is cluster x this)
+cudaError_t va_glv_pair_max_clusters(int stepper, int cluster, int sm_count, int *n)
+{
+    switch (stepper) {
+    case VA_RK_RK4: return max_clusters<TabRK4, false>(cluster, sm_count, n);
+    case VA_RK_CK54: return max_clusters<TabCK54, true>(cluster, sm_count, n);
+    case VA_RK_DOPRI5: return max_clusters<TabDOPRI5, true>(cluster, sm_count, n);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// a.cluster = CTAs per trajectory (2 or 4), a.grid a multiple of it: CTAs [c k, c k + c) form cluster k (one slab per CTA,
+// partial-sum row k)
 cudaError_t va_glv_pair_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;
-    if (a.grid & 1) return cudaErrorInvalidValue;
-    const size_t smem = va_glv_pair_smem();
+    if ((a.cluster != 2 && a.cluster != 4) || a.grid % a.cluster) return cudaErrorInvalidValue;
     switch (a.stepper) {
-    case VA_RK_RK4: return launch<TabRK4, false>(a, st, smem);
-    case VA_RK_CK54: return launch<TabCK54, true>(a, st, smem);
-    case VA_RK_DOPRI5: return launch<TabDOPRI5, true>(a, st, smem);
+    case VA_RK_RK4: return launch<TabRK4, false>(a, st);
+    case VA_RK_CK54: return launch<TabCK54, true>(a, st);
+    case VA_RK_DOPRI5: return launch<TabDOPRI5, true>(a, st);
     }
     return cudaErrorInvalidValue;
 }
