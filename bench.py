@@ -215,55 +215,78 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 
 def side_workload(args):
-    """The other BASELINE configs (single GPU, device-resident): same timing rules, one JSON line, not the contract line."""
+    """The other BASELINE configs (device-resident inputs): same timing rules, one JSON line, not the contract line. Under torchrun
+    the batch is sharded over the ranks exactly like the headline workload (no data-path collective; one all_reduce of the summed
+    gradient in summed mode), time = max over ranks."""
     import torch
+    import torch.distributed as dist
     import vectorizedadjoint_b200 as va
     system, n, stepper, adaptive, tol, ti, tf, dt0, max_steps, objective, stages, desc = WORKLOADS[args.workload]
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    B = args.batch if (not args.workload.startswith("glv256") or args.batch != 1 << 20) else (8192 if args.workload == "glv256" else 2048)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Btot = args.batch if (not args.workload.startswith("glv256") or args.batch != 1 << 20) else (8192 if args.workload == "glv256" else 2048)
+    b0, B = va.shard_range(Btot, rank, world)
     npar = va.npar_of(system, n)
     red = va.REDUCE_SUM if args.reduce == "sum" else va.REDUCE_NONE
     f64 = dict(dtype=torch.float64, device=dev)
     params, x0 = torch.empty(B, npar, **f64), torch.empty(B, n, **f64)
-    va.synth_batch_device(system, n, SEED, 0, B, params, x0)
+    va.synth_batch_device(system, n, SEED, b0, B, params, x0)
     x_final, lam = torch.empty(B, n, **f64), torch.empty(B, 1, n, **f64)
     mu = torch.empty((1, npar) if red == va.REDUCE_SUM else (B, 1, npar), **f64)
     n_acc, n_rej, status = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3))
-    eng = va.Engine(system, n, stepper, adaptive, tol, tol, device=0, max_steps=max_steps)
+    eng = va.Engine(system, n, stepper, adaptive, tol, tol, device=local, max_steps=max_steps)
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
 
     def step():
         eng.call("va_forward_adjoint_batch", B, x0, params, ti, tf, dt0, x_final, lam, mu, objective, red, n_acc, n_rej, status,
                  stream=side.cuda_stream)
+        if world > 1 and red == va.REDUCE_SUM:
+            dist.all_reduce(mu)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 1)):
         step()
-    torch.cuda.synchronize()
-    clocks = ClockSampler(0)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.info()["kernel_launches"]
+    barrier()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    clk = clocks.stop()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item()) / args.steps
+    clk = clocks.stop() if clocks else None
     T, R = int(n_acc.sum(dtype=torch.int64)), int(n_rej.sum(dtype=torch.int64))
     info = eng.info()
-    line = {"metric": f"fwd+adjoint gradients/sec, {args.workload} batch {B}", "value": B / (ms * 1e-3), "unit": "gradients/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "batch_total": B, "reduce": args.reduce}, "gpu_launches": info["kernel_launches"] - l0,
-            "mean_accepted_steps": T / B, "mean_rejected": R / B, "max_accepted_steps": int(n_acc.max()),
+    line = {"metric": f"fwd+adjoint gradients/sec, {args.workload} batch {Btot}", "value": Btot / (ms * 1e-3), "unit": "gradients/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "batch_total": Btot, "reduce": args.reduce, "parallelism": f"batch sharded over {world} GPU(s)"},
+            "gpu_launches": info["kernel_launches"] - l0,
+            "mean_accepted_steps": T / max(B, 1), "mean_rejected": R / max(B, 1), "max_accepted_steps": int(n_acc.max()) if B else 0,
             "failed_trajectories": int((status != 0).sum()), "clocks": clk}
     if system == va.SYS_GLV:
         f_rhs, f_vjp = 2 * n * n + 2 * n, 4 * n * n + 3 * n
-        flops = (stages * T + (stages - 1) * R) * f_rhs + stages * T * f_vjp
-        peak = va.measure_fp64_peak(0)
+        flops = (stages * T + (stages - 1) * R) * f_rhs + stages * T * f_vjp  # this rank's shard
+        peak = va.measure_fp64_peak(local)
         line["roofline"] = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                            "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None}
+                            "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "scope": "rank 0's shard on its GPU"}
         line["kernel"] = info.get("kernel_name")
         if n == 256 and info.get("kernel_name") == "k_glv_ring":
             # ring-streamed kernel: every matrix-vector product re-reads the non-cached rows of the 512 KB matrix from L2/HBM
@@ -290,8 +313,13 @@ def side_workload(args):
             pass
         ach = byts / (ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if hbm else None, "traffic": None,
+                            "scope": "rank 0's shard on its GPU",
                             "note": "checkpoint arena traffic 2*8*(N+1) B per accepted step and trajectory"}
-    print(json.dumps(line), flush=True)
+    eng.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
