@@ -518,6 +518,71 @@ def test_glv256_many_waves_summed_mode(va, monkeypatch, kernel):
     assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
 
 
+def test_glv256_full_size_properties_and_finite_differences(va):
+    """BASELINE config 5 size class (N = 256, tol 1e-8) on device-generated inputs through the cluster kernel: determinism,
+    linearity of the reverse sweep in its seed, summed mode, step-count statistics, a sampled oracle comparison (the generator
+    is bit-identical host/device), and central finite differences of J = sum x_i(tf) (fixed-step RK4, so J is smooth)."""
+    import torch
+    N, B = 256, 1500
+    npar = N * N + N
+    dev = torch.device("cuda:0")
+    p = torch.empty(B, npar, dtype=torch.float64, device=dev)
+    x0 = torch.empty(B, N, dtype=torch.float64, device=dev)
+    va.synth_batch_device(va.SYS_GLV, N, 1234, 0, B, p, x0)
+    mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
+    xf, lam1, mu1 = mk(B, N), torch.ones(B, 1, N, dtype=torch.float64, device=dev), mk(B, 1, npar)
+    na = torch.empty(B, dtype=torch.int32, device=dev)
+    st = torch.empty(B, dtype=torch.int32, device=dev)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        assert e.info()["kernel_name"] == "k_glv_pair"
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf, lam1, mu1, va.OBJ_SEED, va.REDUCE_NONE, na, None, st)
+        lam3, mu3 = torch.full((B, 1, N), -2.5, dtype=torch.float64, device=dev), mk(B, 1, npar)
+        xf2 = mk(B, N)
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf2, lam3, mu3, va.OBJ_SEED, va.REDUCE_NONE)
+        musum = mk(1, npar)
+        lam_s = torch.ones(B, 1, N, dtype=torch.float64, device=dev)
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf2, lam_s, musum, va.OBJ_SEED, va.REDUCE_SUM)
+        mu1b = mk(B, 1, npar)
+        lam1b = torch.ones(B, 1, N, dtype=torch.float64, device=dev)
+        e.call("va_forward_adjoint_batch", B, x0, p, 0.0, 10.0, 1e-3, xf2, lam1b, mu1b, va.OBJ_SEED, va.REDUCE_NONE)
+        torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0
+    assert torch.equal(xf, xf2) and torch.equal(mu1, mu1b) and torch.equal(lam1, lam1b)  # deterministic, bit for bit
+    assert torch.isfinite(mu1).all()
+    assert float((mu3 + 2.5 * mu1).abs().max() / mu1.abs().max()) < 1e-13
+    assert float((lam3 + 2.5 * lam1).abs().max() / lam1.abs().max()) < 1e-13
+    ref_sum = mu1[:, 0].sum(dim=0)
+    assert float((musum[0] - ref_sum).abs().max() / ref_sum.abs().max()) < 1e-11
+    steps = na.cpu().numpy()
+    assert 15 <= steps.min() and steps.max() <= 40, (steps.min(), steps.max())
+    idx = np.array([0, 73, 74, 777, B - 1])  # 74 = second trajectory of pair 0
+    ph = p[idx].cpu().numpy()
+    np.testing.assert_array_equal(ph, np.concatenate([oracle.synth_params(oracle.SYS_GLV, N, 1234, int(i), 1) for i in idx]))
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0[idx].cpu().numpy(), ph, 0.0, 10.0, 1e-3,
+                               objective=oracle.OBJ_SUM, threads=8)
+    np.testing.assert_array_equal(steps[idx], o["n_accept"])
+    assert_close(xf[idx].cpu().numpy(), o["x_final"], what="x(tf)")
+    assert_close(mu1[idx, 0].cpu().numpy(), o["mu"], what="mu")
+    assert_close(lam1[idx, 0].cpu().numpy(), o["lam"], what="lambda")
+    # finite differences, fixed-step RK4 on the same kernel
+    p1 = ph[:1]
+    x1 = x0[idx[:1]].cpu().numpy()
+    ks = [0, 100, 255, 256, 256 + 257, 256 + 256 * 100 + 3, 256 + 256 * 255 + 255]
+    h = 1e-6
+    pp = np.repeat(p1, 2 * len(ks), axis=0)
+    for m, k in enumerate(ks):
+        pp[2 * m, k] += h
+        pp[2 * m + 1, k] -= h
+    with va.Engine(va.SYS_GLV, N, va.RK_RK4, False, max_steps=256) as e:
+        assert e.info()["kernel_name"] == "k_glv_pair"
+        base = e.forward_adjoint(x1, p1, 0.0, 1.0, 0.01, objective=va.OBJ_SUM)
+        pert = e.forward_adjoint(np.repeat(x1, 2 * len(ks), axis=0), pp, 0.0, 1.0, 0.01, objective=va.OBJ_SUM)
+    J = pert["x_final"].sum(axis=1)
+    for m, k in enumerate(ks):
+        fd = (J[2 * m] - J[2 * m + 1]) / (2 * h)
+        assert abs(fd - base["mu"][0, 0, k]) <= 1e-7 * abs(fd) + 5e-9, (k, fd, base["mu"][0, 0, k])
+
+
 def test_backward_in_time_integration(va):
     """dt0 < 0 (tf < ti): odeint's less_with_sign logic is sign-aware (reference lib/include/detail/runge_kutta.hpp:93,98)."""
     B = 64
