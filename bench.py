@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1 << 20, help="total parameter sets (all ranks)")
     ap.add_argument("--reduce", default="sum", choices=["sum", "none"])
     ap.add_argument("--workload", default="glv64", choices=sorted(WORKLOADS), help="glv64 = the headline contract line")
+    ap.add_argument("--species", type=int, default=0, help="with --workload glv256: any other species count (same tolerances; not a BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="parameter sets per reference-arm step (0 = auto)")
@@ -222,6 +223,9 @@ def side_workload(args):
     import torch.distributed as dist
     import vectorizedadjoint_b200 as va
     system, n, stepper, adaptive, tol, ti, tf, dt0, max_steps, objective, stages, desc = WORKLOADS[args.workload]
+    if args.species and args.workload == "glv256":
+        n = args.species
+        desc = f"GLV N={n} (Npar={n * n + n}), cash_karp54 controlled rtol=atol=1e-8, t=[0,10]; not a BASELINE config"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -336,14 +336,19 @@ def test_glv_full_size_properties(va):
 
 
 @pytest.mark.parametrize("N,B,stepper,adaptive,tol,tf,dt0", [(100, 6, 2, True, 1e-8, 10.0, 1e-3), (256, 3, 2, True, 1e-8, 10.0, 1e-3),
-                                                            (256, 2, 3, True, 1e-6, 10.0, 1e-3), (80, 4, 1, False, 0.0, 0.3, 0.01)])
+                                                            (256, 2, 3, True, 1e-6, 10.0, 1e-3), (80, 4, 1, False, 0.0, 0.3, 0.01),
+                                                            (65, 3, 3, True, 1e-6, 10.0, 1e-3), (129, 3, 2, True, 1e-8, 10.0, 1e-3),
+                                                            (255, 2, 2, True, 1e-8, 10.0, 1e-3), (200, 3, 1, False, 0.0, 0.3, 0.01),
+                                                            (300, 2, 2, True, 1e-6, 10.0, 1e-3)])
 def test_glv_large_species_counts_streamed_matrix(va, N, B, stepper, adaptive, tol, tf, dt0):
-    """N > 64 (BASELINE config 5 uses N = 256): the matrix no longer fits one SM's registers and is streamed from L2/HBM."""
+    """N > 64 (BASELINE config 5 uses N = 256): the matrix no longer fits one SM's registers. 65..256 species run on the
+    cluster kernel (two SMs hold the matrix; fewer than 256 species are padded with inert ones, odd N included), larger
+    systems on the streamed-matrix kernel."""
     p = oracle.synth_params(oracle.SYS_GLV, N, 2024, 0, B)
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
     o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_SUM, threads=8)
     with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol) as e:
-        assert e.info()["kernel_family"] == 2
+        assert e.info()["kernel_family"] == 2 and e.info()["kernel_name"] == ("k_glv_pair" if N <= 256 else "k_glv_stream")
         r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
         s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
     assert (r["status"] == 0).all()

@@ -14,7 +14,8 @@ import vectorizedadjoint_b200 as va
 
 for N, stepper, adaptive, tol, n_out, B in [(64, va.RK_CK54, True, 1e-6, 1, 9), (50, va.RK_DOPRI5, True, 1e-5, 2, 5), (64, va.RK_RK4, False, 0.0, 1, 3),
                                             (16, va.RK_CK54, True, 1e-6, 1, 9), (10, va.RK_CK54, True, 1e-6, 2, 7), (5, va.RK_DOPRI5, True, 1e-6, 1, 3),
-                                            (20, va.RK_RK4, False, 0.0, 1, 3), (33, va.RK_CK54, True, 1e-5, 1, 3), (100, va.RK_CK54, True, 1e-5, 1, 2)]:
+                                            (20, va.RK_RK4, False, 0.0, 1, 3), (33, va.RK_CK54, True, 1e-5, 1, 3), (100, va.RK_CK54, True, 1e-5, 1, 2),
+                                            (129, va.RK_CK54, True, 1e-5, 2, 2), (300, va.RK_CK54, True, 1e-5, 1, 1)]:
     p = oracle.synth_params(oracle.SYS_GLV, N, 5, 0, B)
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
     tf, dt0 = (10.0, 1e-3) if adaptive else (0.2, 0.01)

@@ -231,7 +231,9 @@ __device__ __forceinline__ double product_cols(Pair<CL> &P, const double (&creg)
     return y;
 }
 
-template <class Tab, bool ADAPTIVE, int CL>
+// EXACT: a.n == N. Otherwise 64 < a.n < N species are padded with inert ones (x = r = 0, zero matrix rows and columns): the
+// parameter blocks keep their row stride a.n in global memory, the kernel's vectors and step blocks are N wide.
+template <class Tab, bool ADAPTIVE, int CL, bool EXACT>
 __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int HR = Pair<CL>::HR, SR = Pair<CL>::SR;
@@ -250,7 +252,9 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
     double *red = p3buf + P3_STAGES * P3_STAGE_DOUBLES; // [8] error-norm partials
     uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8); // [0]: matrix rows landed (TMA); [1], [2]: exchange; [3..]: phase 3 ring
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int npar = N * N + N;
+    const int n = EXACT ? N : a.n;
+    const int npar = n * n + n;
+    const bool live = tid < n; // this thread's component exists
 
     Pair<CL> P;
     P.rank = cg::this_cluster().block_rank();
@@ -288,10 +292,21 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
 
     for (int64_t b = pair_id; b < a.B; b += n_pairs) {
         const double *pb = a.params + b * npar;
-        const double *Aown = pb + N + (size_t)rank * HR * N; // own rows; [0, SR) -> shared memory, [SR, HR) -> registers
-        const double *Ac = Aown + (size_t)SR * N;
+        const double *Aown = pb + n + (size_t)rank * HR * n; // own rows; [0, SR) -> shared memory, [SR, HR) -> registers
+        const double *Ac = Aown + (size_t)SR * n;
+        const int row0 = (int)rank * HR; // global index of own row 0
         // ------------------------------------------ forward sweep ------------------------------------------------------
-        if (SR > 0 && tid == 0) {
+        if (SR > 0 && !EXACT) {
+            // padded shared-memory rows: thread j fills column j (coalesced), zeros outside the n x n matrix
+            double *scw = sc;
+#pragma unroll 8
+            for (int i = 0; i < SR; ++i) {
+                const bool in = live && row0 + i < n;
+                const double v = __ldg(pb + n + (in ? (size_t)(row0 + i) * n + tid : 0)); // out-of-range lanes read a valid address and discard it
+                scw[(size_t)i * N + tid] = in ? v : 0.0;
+            }
+        }
+        if (SR > 0 && EXACT && tid == 0) {
             mbar_expect_tx(bar, (uint32_t)(SR * N * 8));
 #pragma unroll 1
             for (uint32_t off = 0; off < (uint32_t)(SR * N * 8); off += TMA_PIECE)
@@ -302,14 +317,24 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
-                creg[r * 8 + 2 * k] = t.x;
-                creg[r * 8 + 2 * k + 1] = t.y;
+                if (EXACT) {
+                    const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
+                    creg[r * 8 + 2 * k] = t.x;
+                    creg[r * 8 + 2 * k + 1] = t.y;
+                } else {
+                    const int row = row0 + SR + warp * 8 + r, col = 64 * k + 2 * lane;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const bool in = row < n && col + e < n;
+                        const double v = __ldg(pb + n + (in ? (size_t)row * n + col + e : 0));
+                        creg[r * 8 + 2 * k + e] = in ? v : 0.0;
+                    }
+                }
             }
-        rr[tid] = __ldg(pb + tid);
-        double x = a.x0[b * N + tid];
+        rr[tid] = live ? __ldg(pb + tid) : 0.0;
+        double x = live ? a.x0[b * n + tid] : 0.0;
         P.xin()[tid] = x;
-        if (SR > 0) {
+        if (SR > 0 && EXACT) {
             mbar_wait_or_trap(bar, bar_parity);
             bar_parity ^= 1u;
         }
@@ -370,6 +395,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 for (int j = 0; j < S; ++j)
                     if (Tab::db(j) != 0.0) acc = fma(Tab::db(j), K[j], acc);
                 double e = fabs(dt * acc) / (a.eps_abs + a.eps_rel * (fabs(x) + fabs(dt) * fabs(K[0])));
+                if (!EXACT && !live) e = 0.0; // inert species (0 / 0 when eps_abs = 0)
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, d));
                 __syncthreads(); // previous readers of red are done
@@ -418,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
         status = __syncthreads_or(status); // also: every slab store of the forward sweep is visible to the CTA
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
         if (rank == 0) {
-            a.x_final[b * N + tid] = failed ? nan("") : x;
+            if (live) a.x_final[b * n + tid] = failed ? nan("") : x;
             if (tid == 0) {
                 if (a.n_accept) a.n_accept[b] = T;
                 if (a.n_reject) a.n_reject[b] = rejects;
@@ -429,13 +455,13 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
 
         // ------------------------------------------ reverse sweep ------------------------------------------------------
         for (int o = 0; o < a.n_out; ++o) {
-            double *lam_io = a.lambda + (b * a.n_out + o) * N;
+            double *lam_io = a.lambda + (b * a.n_out + o) * n;
             const bool sum_mode = a.reduce == VA_REDUCE_SUM;
             double *gbar = sum_mode ? a.partial + pair_id * npar : a.mu + (b * a.n_out + o) * npar;
             const bool overwrite = !sum_mode || !row_init; // first use of this accumulator row
             if (failed) {
                 if (rank == 0) {
-                    lam_io[tid] = nan("");
+                    if (live) lam_io[tid] = nan("");
                     if (!sum_mode)
                         for (int k = tid; k < npar; k += NT) gbar[k] = nan("");
                 }
@@ -443,8 +469,16 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             }
             // ---- phase 2: state adjoint ----
 #pragma unroll
-            for (int i = 0; i < CR; ++i) creg[i] = __ldg(Ac + (size_t)i * N + tid); // column layout
-            double lam = a.objective == VA_OBJ_SUM ? 1.0 : a.objective == VA_OBJ_HALF_NORM2 ? x : lam_io[tid];
+            for (int i = 0; i < CR; ++i) { // column layout
+                if (EXACT) {
+                    creg[i] = __ldg(Ac + (size_t)i * N + tid);
+                } else {
+                    const bool in = live && row0 + SR + i < n;
+                    const double v = __ldg(pb + n + (in ? (size_t)(row0 + SR + i) * n + tid : 0));
+                    creg[i] = in ? v : 0.0;
+                }
+            }
+            double lam = !live ? 0.0 : a.objective == VA_OBJ_SUM ? 1.0 : a.objective == VA_OBJ_HALF_NORM2 ? x : lam_io[tid];
             double rbar = 0.0;
             double t_hi = t_final;
 #pragma unroll 1
@@ -478,7 +512,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 }
                 lam = W[0];
             }
-            if (rank == 0) {
+            if (rank == 0 && live) {
                 lam_io[tid] = lam;
                 if (overwrite) gbar[tid] = rbar;
                 else atomicAdd(gbar + tid, rbar);
@@ -504,7 +538,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 }
             };
 #pragma unroll 1
-            for (int cb = (int)rank * HR; cb < (int)rank * HR + HR; cb += PCOLS) {
+            for (int cb = (int)rank * HR; cb < (int)rank * HR + HR && cb < n; cb += PCOLS) {
                 double acc[8][8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
@@ -546,12 +580,22 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        double *dst = gbar + N + (size_t)(8 * ty + r) * N + cb + 16 * q + 2 * tx;
-                        if (overwrite) {
-                            *reinterpret_cast<double2 *>(dst) = make_double2(acc[r][2 * q], acc[r][2 * q + 1]);
+                        const int row = 8 * ty + r, col = cb + 16 * q + 2 * tx;
+                        double *dst = gbar + n + (size_t)row * n + col;
+                        if (EXACT) {
+                            if (overwrite) {
+                                *reinterpret_cast<double2 *>(dst) = make_double2(acc[r][2 * q], acc[r][2 * q + 1]);
+                            } else {
+                                atomicAdd(dst, acc[r][2 * q]);
+                                atomicAdd(dst + 1, acc[r][2 * q + 1]);
+                            }
                         } else {
-                            atomicAdd(dst, acc[r][2 * q]);
-                            atomicAdd(dst + 1, acc[r][2 * q + 1]);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (row < n && col + e < n) {
+                                    if (overwrite) dst[e] = acc[r][2 * q + e];
+                                    else atomicAdd(dst + e, acc[r][2 * q + e]);
+                                }
                         }
                     }
             }
@@ -575,7 +619,9 @@ template <class Tab, bool ADAPTIVE, int CL>
 cudaError_t configure(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &at, int grid, cudaStream_t st)
 {
     const size_t smem = smem_bytes<Tab, ADAPTIVE, CL>();
-    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -597,7 +643,8 @@ cudaError_t launch2(const VaGlvWideArgs &a, cudaStream_t st)
     cudaLaunchAttribute at;
     cudaError_t e = configure<Tab, ADAPTIVE, CL>(cfg, at, a.grid, st);
     if (e != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL>, a);
+    return a.n == N ? cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, true>, a)
+                    : cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, false>, a);
 }
 template <class Tab, bool ADAPTIVE>
 cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st)
@@ -611,7 +658,7 @@ cudaError_t max_clusters2(int sm_count, int *n)
     cudaLaunchAttribute at;
     cudaError_t e = configure<Tab, ADAPTIVE, CL>(cfg, at, sm_count / CL * CL, nullptr);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveClusters(n, k_glv_pair<Tab, ADAPTIVE, CL>, &cfg);
+    return cudaOccupancyMaxActiveClusters(n, k_glv_pair<Tab, ADAPTIVE, CL, true>, &cfg);
 }
 template <class Tab, bool ADAPTIVE>
 cudaError_t max_clusters(int cl, int sm_count, int *n)
@@ -623,7 +670,7 @@ cudaError_t max_clusters(int cl, int sm_count, int *n)
 
 bool va_glv_pair_supported(int n, int stepper, int adaptive)
 {
-    if (n != N) return false;
+    if (n <= 64 || n > N) return false; // <= 64 species: the register kernels (va_glv_t8.cu, va_glv_wide.cu)
     if (stepper == VA_RK_RK4) return !adaptive;
     if (stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5) return adaptive != 0;
     return false;
