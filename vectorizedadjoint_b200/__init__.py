@@ -24,7 +24,7 @@ __all__ = ["Engine", "EngineError", "lib", "build", "SYS_HARMONIC", "SYS_VANDERP
            "measure_fp64_peak", "measure_hbm_copy", "npar_of", "shard_range"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libva_engine.so")
+LIB_PATH = os.environ.get("VA_ENGINE_LIB") or os.path.join(HERE, "libva_engine.so")  # VA_ENGINE_LIB: experiment builds
 
 SYS_HARMONIC, SYS_VANDERPOL, SYS_GLV, SYS_TAPE = 0, 1, 2, 3
 RK_EULER, RK_RK4, RK_CK54, RK_DOPRI5, RK_RKF78 = 0, 1, 2, 3, 4

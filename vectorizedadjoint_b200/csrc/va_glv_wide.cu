@@ -47,6 +47,9 @@
 
 namespace {
 
+#ifndef VA_GLV_MINB16
+#define VA_GLV_MINB16 5 // resident 128-thread CTAs per SM the NP = 16 instantiation is sized for (build knob GLV_MINB16)
+#endif
 constexpr int NPMAX = 64; // largest padded species count of this kernel family
 constexpr int HDR = 8;   // doubles in a step-block header (hdr[0] = t_n)
 
@@ -121,7 +124,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // threads (NP = 64, LG = 8: 128 threads with 4x8 / 8x4 tiles; NP = 16, LG = 8: ONE WARP with 4x2 / 2x4 tiles), and a CTA
 // hosts TPC = 128 / NTT independent trajectories ("slots"), each with its own shared buffers, barrier and slab.
 template <class Tab, bool ADAPTIVE, bool EXACT, int LG, int NP>
-__global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : 5) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
+__global__ void __launch_bounds__(128, NP == 64 ? VA_GLV_MINB : NP == 32 ? 3 : VA_GLV_MINB16) k_glv_wide(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int NTT = (NP / 4) * LG; // threads per trajectory
     constexpr int NT = 128;            // threads per CTA
