@@ -420,6 +420,77 @@ def test_glv_register_kernel_generations_agree(va, monkeypatch, N, B):
     assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-11, what="mu")
 
 
+@pytest.mark.parametrize("N,B,stepper,adaptive,tol,tf,dt0", [(16, 300, 2, True, 1e-8, 10.0, 1e-3), (16, 40, 3, True, 1e-6, 10.0, 1e-3),
+                                                            (10, 37, 2, True, 1e-8, 10.0, 1e-3), (13, 9, 3, True, 1e-7, 10.0, 1e-3),
+                                                            (5, 33, 2, True, 1e-5, 10.0, 1e-3), (16, 21, 1, False, 0.0, 0.3, 0.01),
+                                                            (3, 5, 2, True, 1e-8, 3.0, 1e-3)])
+def test_glv_quad_kernel_agrees_with_first_generation_and_oracle(va, monkeypatch, N, B, stepper, adaptive, tol, tf, dt0):
+    """Up to 16 species run on va_glv_quad.cu (four lanes per trajectory, eight trajectories per warp in lock step, three
+    phases); VA_GLV_NO_QUAD selects the first-generation kernel (va_glv_wide.cu, a warp per trajectory). Independent
+    thread/data maps of the same algorithm: cross-check them and the oracle, with trajectories of different step counts
+    sharing a warp, idle quads, padded species counts, two seeds, the summed mode and ti == tf."""
+    p = oracle.synth_params(oracle.SYS_GLV, N, 606, 0, B)
+    p[::3, :N] *= 3.0  # spread the growth rates so that neighbouring trajectories take different numbers of steps
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(3).standard_normal((B, 2, N))
+    res = []
+    for quad in (True, False):
+        if not quad:
+            monkeypatch.setenv("VA_GLV_NO_QUAD", "1")
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, n_out=2) as e:
+            assert e.info()["kernel_name"] == ("k_glv_quad" if quad else "k_glv_wide")
+            r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds)
+            s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+            z = e.forward_adjoint(x0, p, 2.0, 2.0, dt0, objective=va.OBJ_SEED, seeds=seeds)  # ti == tf: no step at all
+            e.forward(x0[:50], p[:50], 0.0, tf, dt0)
+            t, x = e.checkpoints(min(B, 50) - 1)
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol) as e:
+            h = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_HALF_NORM2)
+            hs = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_HALF_NORM2, reduce=va.REDUCE_SUM)
+        assert (r["status"] == 0).all() and (z["n_accept"] == 0).all()
+        np.testing.assert_array_equal(z["x_final"], x0)
+        np.testing.assert_array_equal(z["lam"], seeds)
+        assert (z["mu"] == 0).all()
+        assert_close(s["mu"], r["mu"].sum(axis=0), rtol=1e-11, what="mu sum")
+        assert_close(hs["mu"], h["mu"].sum(axis=0), rtol=1e-11, what="mu sum (native summed mode)")
+        assert len(t) == r["n_accept"][min(B, 50) - 1] + 1 and t[0] == 0.0
+        np.testing.assert_array_equal(x[0], x0[min(B, 50) - 1])
+        res.append((r, h))
+    (a, ha), (b, hb) = res
+    np.testing.assert_array_equal(a["n_accept"], b["n_accept"])
+    assert_close(a["x_final"], b["x_final"], rtol=1e-12, what="x(tf)")
+    assert_close(a["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-10, what="lambda")
+    assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-10, what="mu")
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_HALF_NORM2, threads=8)
+    np.testing.assert_array_equal(ha["n_accept"], o["n_accept"])
+    assert_close(ha["x_final"], o["x_final"], what="x(tf)")
+    assert_close(ha["lam"][:, 0], o["lam"], what="lambda")
+    assert_close(ha["mu"][:, 0], o["mu"], what="mu")
+    assert_close(hb["mu"][:, 0], o["mu"], what="mu (first generation)")
+
+
+def test_glv16_several_trajectories_per_quad(va):
+    """More parameter sets than resident quads (148 x 64 on a B200): every quad integrates several trajectories and, in summed
+    mode, keeps adding to its partial-sum row; replicated parameter sets must give identical rows wherever they run."""
+    N, B = 16, 30000
+    base = oracle.synth_params(oracle.SYS_GLV, N, 99, 0, 7)
+    p = base[np.arange(B) % 7]
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        assert e.info()["kernel_name"] == "k_glv_quad"
+        r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+        s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+    assert (r["status"] == 0).all()
+    for k in range(7):
+        np.testing.assert_array_equal(r["mu"][k::7], np.broadcast_to(r["mu"][k], r["mu"][k::7].shape))
+        np.testing.assert_array_equal(r["lam"][k::7], np.broadcast_to(r["lam"][k], r["lam"][k::7].shape))
+        np.testing.assert_array_equal(r["x_final"][k::7], np.broadcast_to(r["x_final"][k], r["x_final"][k::7].shape))
+    assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0[:7], p[:7], 0.0, 10.0, 1e-3, objective=oracle.OBJ_SUM)
+    np.testing.assert_array_equal(r["n_accept"][:7], o["n_accept"])
+    assert_close(r["mu"][:7, 0], o["mu"], what="mu")
+
+
 def test_glv_streamed_family_agrees_with_register_family(va, monkeypatch):
     """The two GLV kernel families are independent implementations: cross-check them at N = 64."""
     N, B = 64, 40

@@ -44,6 +44,13 @@ int va_glv_t8_block_doubles(int stepper, int n_out);
 cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);
 cudaError_t va_glv_t8_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
+// quad kernel for up to 16 species (va_glv_quad.cu): four lanes per trajectory, eight trajectories per warp, three phases
+bool va_glv_quad_supported(int n, int stepper, int adaptive);
+int va_glv_quad_block_doubles(int stepper, int n_out);
+int va_glv_quad_slots_per_cta();
+int va_glv_quad_threads();
+cudaError_t va_glv_quad_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
 // streamed-matrix GLV family (va_glv_stream.cu): any N, one 256-thread CTA per trajectory, same argument block
 bool va_glv_stream_supported(int n, int stepper, int adaptive);
 int va_glv_stream_block_doubles(int n, int stepper, int recompute);

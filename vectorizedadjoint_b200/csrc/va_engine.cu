@@ -80,6 +80,7 @@ struct va_engine {
     // wide family
     int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
     bool t8 = false;  // FAM_GLV_WIDE served by va_glv_t8.cu (33..64 species)
+    bool quad = false; // FAM_GLV_WIDE served by va_glv_quad.cu (up to 16 species)
     int glv_blk = 0;  // doubles per step block of the register-kernel slab
     bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
     int ring_flags = 0;
@@ -231,7 +232,8 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
             a.reduce = native_sum ? VA_REDUCE_SUM : VA_REDUCE_NONE;
             a.mu = d.mu;
         }
-        if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
+        if (e->family == FAM_GLV_WIDE && e->quad) VA_CUDA(va_glv_quad_forward_adjoint(a, st));
+        else if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
         else if (e->pairk) VA_CUDA(va_glv_pair_forward_adjoint(a, st));
         else if (e->ring) {
@@ -518,8 +520,19 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
     } else if (family == FAM_GLV_WIDE) {
         // 33..64 species: second-generation kernel (va_glv_t8.cu); VA_GLV_V1 keeps the first generation for cross-checks
         e->t8 = va_glv_t8_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_V1");
+        // up to 16 species: quad kernel (va_glv_quad.cu); VA_GLV_NO_QUAD keeps the first-generation kernel for cross-checks
+        e->quad = va_glv_quad_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_NO_QUAD") && !getenv("VA_GLV_V1");
         cudaError_t ce;
-        if (e->t8) {
+        if (e->quad) {
+            ce = cudaSuccess;
+            e->ctas_per_sm = 1;
+            e->grid = e->sm_count;
+            e->threads = va_glv_quad_threads();
+            e->tpc = va_glv_quad_slots_per_cta();
+            e->pair = 1;
+            e->glv_blk = va_glv_quad_block_doubles(desc->stepper, desc->n_out);
+            e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+        } else if (e->t8) {
             ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
             e->pair = 1;
             e->glv_blk = va_glv_t8_block_doubles(desc->stepper, desc->n_out);
@@ -592,7 +605,7 @@ int va_engine_get_info(va_engine *e, va_engine_info *info)
     info->chunk_trajectories = e->chunk_traj;
     info->kernel_launches = e->launches;
     info->last_kernel_ms = e->last_ms;
-    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->t8 ? "k_glv_t8" : "k_glv_wide")
+    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->quad ? "k_glv_quad" : e->t8 ? "k_glv_t8" : "k_glv_wide")
                      : e->pairk ? "k_glv_pair" : e->ring ? "k_glv_ring" : "k_glv_stream";
     std::snprintf(info->kernel_name, sizeof(info->kernel_name), "%s", kn);
     cudaDeviceProp prop;
