@@ -33,6 +33,11 @@ constexpr int QPC = NT / 4;          // trajectories (quads) per CTA
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SADJ_MAX = 6;
 constexpr int BUF = HDR + 2 * SADJ_MAX * NP; // doubles per shared-memory block buffer (header, X section, g or v section)
+// shared memory per quad; 16 bytes more than a multiple of 128: the eight quads of a warp broadcast-read eight different
+// 16-byte bank groups (one wavefront per LDS.128; with a multiple of 128 every operand load was an 8-way bank conflict and
+// the LSU data path 86 % busy)
+constexpr int QSTRIDE = 2 * NP + 2 * BUF + 2;
+static_assert((QSTRIDE * 8) % 128 == 16, "bank-group skew between the quads of a warp");
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(FULL, v, m); }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
@@ -52,7 +57,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_quad(const __grid_constant__ VaGl
     extern __shared__ __align__(128) double sm_all[]; // per quad: xs[2][NP] exchange buffers, bb[2][BUF] block buffers
     const int lane = threadIdx.x & 31, q = lane & 3;
     const int qc = threadIdx.x >> 2; // quad inside the CTA
-    double *const xs = sm_all + (size_t)qc * (2 * NP + 2 * BUF);
+    double *const xs = sm_all + (size_t)qc * QSTRIDE;
     double *const bb = xs + 2 * NP;
     const int n = EXACT ? NP : a.n;
     const int npar = n * n + n;
@@ -79,15 +84,20 @@ __global__ void __launch_bounds__(NT, 1) k_glv_quad(const __grid_constant__ VaGl
     // y_k = sum_c M[k][c] vec[c] for the lane's four rows, vec = the vector just put
     auto dot = [&](const double(&M)[4][NP], double(&y)[4]) {
         const double2 *s2 = reinterpret_cast<const double2 *>(xs + p * NP);
+        double z[4]; // second chain per row: the dependent chains are 8 DFMAs long instead of 16
 #pragma unroll
-        for (int c = 0; c < NP / 2; ++c) {
-            const double2 v = s2[c];
+        for (int c = 0; c < NP / 2; c += 2) {
+            const double2 v = s2[c], w = s2[c + 1];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 y[k] = c == 0 ? M[k][0] * v.x : fma(M[k][2 * c], v.x, y[k]);
+                z[k] = c == 0 ? M[k][2] * w.x : fma(M[k][2 * c + 2], w.x, z[k]);
                 y[k] = fma(M[k][2 * c + 1], v.y, y[k]);
+                z[k] = fma(M[k][2 * c + 3], w.y, z[k]);
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] += z[k];
         p ^= 1;
     };
     // one step block (header + X section, and the g or v section) -> shared-memory buffer `which`, 16 bytes per cp.async
@@ -491,7 +501,7 @@ int va_glv_quad_threads() { return NT; }
 cudaError_t va_glv_quad_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;
-    const size_t smem = (size_t)QPC * (2 * NP + 2 * BUF) * 8;
+    const size_t smem = (size_t)QPC * QSTRIDE * 8;
     switch (a.stepper) {
     case VA_RK_RK4: return launch<TabRK4, false>(a, st, smem);
     case VA_RK_CK54: return launch<TabCK54, true>(a, st, smem);
