@@ -73,3 +73,19 @@ def test_torch_front_end_imports_and_fails_loudly_without_gpu():
         pytest.skip("CUDA device present")
     with pytest.raises(va.EngineError):
         torch_api.OdeSolver(va.SYS_HARMONIC, 2, va.RK_RK4, False, ti=0.0, tf=1.0, dt0=0.01)
+
+
+def test_headline_kernel_compiles_without_spills(va):
+    """The GLV N = 64 kernel (va_glv_t8.cu, cash_karp54, adaptive, exact species count) is register-tuned to 252 registers and
+    no spills; unrelated edits have broken that before (new fields in front of `coef` in VaGlvWideArgs moved constant-bank
+    offsets: 104 bytes of spills, -4 % throughput). The ptxas log of the in-tree build is the witness."""
+    log = os.path.join(ROOT, "vectorizedadjoint_b200", "csrc", "build", "va_glv_t8.ptxas.log")
+    if not os.path.exists(log):
+        va.build()
+    if not os.path.exists(log):
+        pytest.skip("no in-tree build log (library built elsewhere)")
+    text = open(log).read()
+    m = re.search(r"Function properties for \S*k_glv_t8INS_7TabCK54ELb1ELb1E\S*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads",
+                  text)
+    assert m, "headline instantiation not found in the ptxas log"
+    assert (int(m.group(2)), int(m.group(3))) == (0, 0), f"k_glv_t8<TabCK54, adaptive, exact> spills: {m.group(0)}"

@@ -26,9 +26,11 @@ struct VaGlvWideArgs {
     int grid;
     int blk_doubles;      // va_glv_t8.cu: doubles per step block (the v section is separate when n_out > 1)
     int recompute;        // streamed family: 1 = keep only (t_n, x_n) and recompute the stages in the reverse sweep
+    struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
+    // Fields added after the headline kernel was tuned go HERE, behind everything va_glv_t8.cu reads: inserting them above
+    // moved the constant-bank offsets of `coef` and cost that kernel 3 registers, 104 bytes of spills and 4 % (5.92 -> 5.66 M).
     int cluster;          // cluster kernel (va_glv_pair.cu): CTAs per trajectory (2 or 4)
     int flags;            // ring kernel: bit 1 = evict_last policy on the matrix stream, bit 2 = no register-cached rows
-    struct { double a[7][6], b[7], db[7]; } coef; // tableau values, filled by the launcher
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);
