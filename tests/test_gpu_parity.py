@@ -469,6 +469,23 @@ def test_glv_quad_kernel_agrees_with_first_generation_and_oracle(va, monkeypatch
     assert_close(hb["mu"][:, 0], o["mu"], what="mu (first generation)")
 
 
+def test_glv_quad_large_step_capacity_shrinks_the_grid(va):
+    """64 checkpoint slabs per CTA: a large max_steps must not exhaust HBM; the engine runs fewer CTAs instead, results unchanged."""
+    N, B = 16, 200
+    p = oracle.synth_params(oracle.SYS_GLV, N, 17, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    out = []
+    for cap, frac in ((0, 0.0), (2000, 0.05)):  # 9472 slabs x 2001 blocks x 1600 B = 30 GB > 5 % of HBM -> fewer CTAs
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, max_steps=cap, workspace_fraction=frac) as e:
+            info = e.info()
+            assert info["kernel_name"] == "k_glv_quad"
+            r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+            assert e.info()["workspace_bytes"] < 10e9
+        out.append(r)
+    np.testing.assert_array_equal(out[0]["mu"], out[1]["mu"])
+    np.testing.assert_array_equal(out[0]["x_final"], out[1]["x_final"])
+
+
 def test_glv16_several_trajectories_per_quad(va):
     """More parameter sets than resident quads (148 x 64 on a B200): every quad integrates several trajectories and, in summed
     mode, keeps adding to its partial-sum row; replicated parameter sets must give identical rows wherever they run."""

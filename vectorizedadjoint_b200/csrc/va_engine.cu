@@ -532,6 +532,12 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
             e->pair = 1;
             e->glv_blk = va_glv_quad_block_doubles(desc->stepper, desc->n_out);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+            // 64 slabs per CTA: a large step capacity (max_steps) must not exhaust HBM -- run fewer CTAs instead
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const double frac = desc->workspace_fraction > 0 ? desc->workspace_fraction : 0.5;
+                while (e->grid > 1 && (double)e->grid * e->tpc * e->slab_stride * 8.0 > frac * (double)free_b) e->grid = (e->grid + 1) / 2;
+            }
         } else if (e->t8) {
             ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
             e->pair = 1;
