@@ -374,7 +374,7 @@ def test_glv_checkpoint_policy_recompute_matches_store_stages(va, N, B, stepper,
             info = e.info()
             assert info["ckpt_policy"] == pol
             if pol == va.CKPT_RECOMPUTE:
-                assert info["kernel_family"] == 2
+                assert info["kernel_family"] == 2 and info["kernel_name"] == ("k_glv_pair" if 64 < N <= 256 else "k_glv_stream")
             res[pol] = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
             e.forward(x0, p, 0.0, tf, dt0)
             t, x = e.checkpoints(1)
@@ -387,6 +387,69 @@ def test_glv_checkpoint_policy_recompute_matches_store_stages(va, N, B, stepper,
         assert len(t) == r["n_accept"][1] + 1 and t[0] == 0.0
         np.testing.assert_array_equal(x[0], x0[1])
     assert_close(res[va.CKPT_RECOMPUTE]["mu"], res[va.CKPT_STORE_STAGES]["mu"], rtol=1e-11, what="mu, recompute vs store")
+
+
+@pytest.mark.parametrize("seg", ["1", "4", "16", "64"])
+def test_glv256_recompute_policy_segments_on_the_cluster_kernel(va, monkeypatch, seg):
+    """Recompute policy on the cluster kernel: the forward sweep keeps (t_n, x_n) only, the reverse sweep re-integrates segments
+    of VA_PAIR_SEG steps (newest first) and sweeps back through each. Segment lengths that divide the step count, do not divide
+    it, and exceed it; two seeds, summed mode, both objectives; against the store-stages policy, the oracle and the checkpoints."""
+    N, B = 256, 4
+    p = oracle.synth_params(oracle.SYS_GLV, N, 8080, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(11).standard_normal((B, 2, N))
+    monkeypatch.setenv("VA_PAIR_SEG", seg)
+    res = {}
+    for pol in (va.CKPT_RECOMPUTE, va.CKPT_STORE_STAGES):
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=2, ckpt_policy=pol) as e:
+            info = e.info()
+            assert info["kernel_name"] == "k_glv_pair" and info["ckpt_policy"] == pol
+            r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+            s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+            z = e.forward_adjoint(x0, p, 2.0, 2.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+            e.forward(x0, p, 0.0, 10.0, 1e-3)
+            t, x = e.checkpoints(3)
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, ckpt_policy=pol) as e:
+            h = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2)
+            hs = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_HALF_NORM2, reduce=va.REDUCE_SUM)
+        assert (r["status"] == 0).all() and (z["n_accept"] == 0).all()
+        np.testing.assert_array_equal(z["lam"], seeds)
+        assert (z["mu"] == 0).all()
+        assert_close(s["mu"], r["mu"].sum(axis=0), rtol=1e-11, what="mu sum")
+        assert_close(hs["mu"], h["mu"].sum(axis=0), rtol=1e-11, what="mu sum (native summed mode)")
+        assert len(t) == r["n_accept"][3] + 1 and t[0] == 0.0 and abs(t[-1] - 10.0) < 1e-12
+        np.testing.assert_array_equal(x[0], x0[3])
+        res[pol] = (r, h, t, x)
+    (a, ha, ta, xa), (b, hb, tb, xb) = res[va.CKPT_RECOMPUTE], res[va.CKPT_STORE_STAGES]
+    np.testing.assert_array_equal(a["n_accept"], b["n_accept"])
+    np.testing.assert_array_equal(a["x_final"], b["x_final"])  # the forward sweeps are the same code
+    np.testing.assert_array_equal(ta, tb)
+    np.testing.assert_array_equal(xa, xb)
+    assert_close(a["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-10, what="lambda")
+    assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-10, what="mu")
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, 1e-8, 1e-8, x0, p, 0.0, 10.0, 1e-3,
+                               objective=oracle.OBJ_HALF_NORM2, threads=8)
+    np.testing.assert_array_equal(ha["n_accept"], o["n_accept"])
+    assert_close(ha["lam"][:, 0], o["lam"], what="lambda")
+    assert_close(ha["mu"][:, 0], o["mu"], what="mu")
+
+
+def test_glv_auto_policy_long_horizon_uses_the_cluster_kernel(va):
+    """VA_CKPT_AUTO with a step capacity whose stage blocks would not fit the workspace share of HBM: the engine chooses the
+    recompute policy and stays on the cluster kernel (state store + segment re-integration); results as with stored stages."""
+    N, B = 200, 3
+    p = oracle.synth_params(oracle.SYS_GLV, N, 12, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-12, 1e-12, max_steps=1000, workspace_fraction=0.01) as e:
+        info = e.info()  # 148 x 1001 x 36.9 KB = 5.5 GB of stage blocks > 1 % of HBM
+        assert info["kernel_name"] == "k_glv_pair" and info["ckpt_policy"] == va.CKPT_RECOMPUTE
+        r = e.forward_adjoint(x0, p, 0.0, 1000.0, 1e-3, objective=va.OBJ_SUM)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-12, 1e-12, max_steps=1000, ckpt_policy=va.CKPT_STORE_STAGES) as e:
+        q = e.forward_adjoint(x0, p, 0.0, 1000.0, 1e-3, objective=va.OBJ_SUM)
+    assert (r["status"] == 0).all() and r["n_accept"].min() > 100
+    np.testing.assert_array_equal(r["n_accept"], q["n_accept"])
+    assert_close(r["mu"][:, 0], q["mu"][:, 0], rtol=1e-9, what="mu")
+    assert_close(r["lam"][:, 0], q["lam"][:, 0], rtol=1e-9, what="lambda")
 
 
 @pytest.mark.parametrize("N,B", [(64, 5), (50, 3), (64, 1)])

@@ -27,17 +27,18 @@ for N, stepper, adaptive, tol, n_out, B in [(64, va.RK_CK54, True, 1e-6, 1, 9), 
     assert (r["status"] == 0).all()
     print(N, "family", info["kernel_family"], info["kernel_name"], "threads", info["threads_per_cta"], "steps", r["n_accept"].tolist(), flush=True)
 # 256 species: cluster-pair kernel (DSMEM exchange, TMA loads), ring-streamed kernel, plain streamed kernel
-for env, B in [({}, 3), ({"VA_GLV_NO_PAIR": "1"}, 2), ({"VA_GLV_NO_RING": "1"}, 1)]:
+for env, B in [({}, 3), ({"VA_TEST_POLICY": "2", "VA_PAIR_SEG": "3"}, 2), ({"VA_GLV_NO_PAIR": "1", "VA_TEST_POLICY": "0"}, 2), ({"VA_GLV_NO_RING": "1"}, 1)]:
     os.environ.update(env)
+    policy = int(os.environ.get("VA_TEST_POLICY", "0"))  # 2 = recompute (cluster kernel: state store + segment re-integration)
     p = oracle.synth_params(oracle.SYS_GLV, 256, 5, 0, B)
     x0 = oracle.synth_x0(oracle.SYS_GLV, 256, p)
     seeds = np.random.default_rng(0).standard_normal((B, 2, 256))
-    with va.Engine(va.SYS_GLV, 256, va.RK_CK54, True, 1e-5, 1e-5, n_out=2) as e:
+    with va.Engine(va.SYS_GLV, 256, va.RK_CK54, True, 1e-5, 1e-5, n_out=2, ckpt_policy=policy) as e:
         r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
         s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
         info = e.info()
     assert (r["status"] == 0).all()
-    print(256, info["kernel_name"], "steps", r["n_accept"].tolist(), flush=True)
+    print(256, info["kernel_name"], "policy", info["ckpt_policy"], "steps", r["n_accept"].tolist(), flush=True)
 # thread-per-trajectory family: Van der Pol (all adaptive steppers), harmonic oscillator (fixed step), waves + summed mode
 for system, stepper, adaptive, tol, tf, dt0, B in [(va.SYS_VANDERPOL, va.RK_DOPRI5, True, 1e-6, 0.5, 1e-3, 300), (va.SYS_VANDERPOL, va.RK_RKF78, True, 1e-6, 0.5, 1e-3, 70),
                                                    (va.SYS_VANDERPOL, va.RK_CK54, True, 1e-5, 0.5, 1e-3, 33), (va.SYS_HARMONIC, va.RK_RK4, False, 0.0, 1.0, 0.01, 129)]:

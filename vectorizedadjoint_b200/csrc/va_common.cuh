@@ -31,6 +31,11 @@ struct VaGlvWideArgs {
     // moved the constant-bank offsets of `coef` and cost that kernel 3 registers, 104 bytes of spills and 4 % (5.92 -> 5.66 M).
     int cluster;          // cluster kernel (va_glv_pair.cu): CTAs per trajectory (2 or 4)
     int flags;            // ring kernel: bit 1 = evict_last policy on the matrix stream, bit 2 = no register-cached rows
+    // cluster kernel, recompute policy (a.recompute != 0): per-CTA state store of (cap + 1) entries [8-double header (t_n) | x_n]
+    // and the segment length (steps re-integrated at a time; the slab then holds seg_len blocks)
+    double *xstore;
+    int64_t xstore_stride;
+    int seg_len;
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);

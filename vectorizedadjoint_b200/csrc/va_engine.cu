@@ -86,6 +86,10 @@ struct va_engine {
     int ring_flags = 0;
     bool pairk = false; // FAM_GLV_STREAM served by va_glv_pair.cu (256 species, matrix on chip in a cluster of pair_cl CTAs)
     int pair_cl = 2;
+    bool pair_seg = false; // ... under the recompute policy: per-CTA state store + segment re-integration
+    int pair_seg_len = 16;
+    int64_t xstore_stride = 0;
+    DevBuf xstore;
     int64_t slab_stride = 0;
     DevBuf slab, partial;
     // scalar family
@@ -120,7 +124,9 @@ int ensure_workspace(va_engine *e, int64_t B)
         const size_t need = (size_t)e->grid * e->tpc * e->pair * e->slab_stride * 8;
         if (int rc = e->slab.ensure(need)) return rc;
         if (int rc = e->partial.ensure((size_t)e->grid * e->tpc * e->desc.n_par * 8)) return rc;
-        e->workspace_bytes = (int64_t)(e->slab.bytes + e->partial.bytes);
+        if (e->pair_seg)
+            if (int rc = e->xstore.ensure((size_t)e->grid * e->xstore_stride * 8)) return rc;
+        e->workspace_bytes = (int64_t)(e->slab.bytes + e->partial.bytes + e->xstore.bytes);
         e->chunk_traj = B;
         return VA_OK;
     }
@@ -220,6 +226,11 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.grid = (int)std::min<int64_t>(e->grid, (d.B + e->tpc - 1) / e->tpc);
         if (e->pairk) a.grid = e->pair_cl * (int)std::min<int64_t>(e->grid / e->pair_cl, d.B); // pair_cl CTAs per trajectory
         a.cluster = e->pair_cl;
+        if (e->pair_seg) {
+            a.xstore = e->xstore.as<double>();
+            a.xstore_stride = e->xstore_stride;
+            a.seg_len = e->pair_seg_len;
+        }
         a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE;
         a.blk_doubles = e->glv_blk;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
@@ -474,21 +485,21 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
         e->tpc = 1;
         // checkpoint policy (north_star item 4): STORE_STAGES unless the caller asks for RECOMPUTE, or (AUTO) the slabs of
         // all resident CTAs at the requested capacity would take more than the workspace share of free HBM
+        // 65..256 species: the cluster kernel (va_glv_pair.cu, matrix on chip) under either policy; VA_GLV_NO_PAIR selects the
+        // ring-streamed kernel (256 species, store-stages only), VA_GLV_NO_RING the plain streamed kernel
+        e->pairk = va_glv_pair_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_NO_PAIR") &&
+                   !getenv("VA_GLV_NO_RING") && e->sm_count >= 2;
         int policy = desc->ckpt_policy;
         if (policy == VA_CKPT_AUTO) {
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             const double frac = desc->workspace_fraction > 0 ? desc->workspace_fraction : 0.5;
-            const double need = (double)e->grid * (e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, 0) * 8.0;
+            const double need = e->pairk ? (double)e->sm_count * (e->cap + 1) * va_glv_pair_block_doubles(desc->stepper) * 8.0
+                                         : (double)e->grid * (e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, 0) * 8.0;
             policy = need > frac * (double)free_b ? VA_CKPT_RECOMPUTE : VA_CKPT_STORE_STAGES;
         }
         e->desc.ckpt_policy = policy;
         e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, policy == VA_CKPT_RECOMPUTE);
-        // 256 species, store-stages: the ring-streamed kernel (va_glv_ring.cu); VA_GLV_NO_RING keeps the plain streamed kernel
-        // 256 species, store-stages: the cluster-pair kernel (va_glv_pair.cu, matrix on chip); VA_GLV_NO_PAIR selects the
-        // ring-streamed kernel, VA_GLV_NO_RING the plain streamed kernel
-        e->pairk = policy == VA_CKPT_STORE_STAGES && va_glv_pair_supported(desc->n_state, desc->stepper, desc->adaptive) &&
-                   !getenv("VA_GLV_NO_PAIR") && !getenv("VA_GLV_NO_RING") && e->sm_count >= 2;
         e->ring = !e->pairk && policy == VA_CKPT_STORE_STAGES && va_glv_ring_supported(desc->n_state, desc->stepper, desc->adaptive) &&
                   !getenv("VA_GLV_NO_RING");
         if (e->pairk) {
@@ -502,6 +513,15 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
             if (getenv("VA_DEBUG")) fprintf(stderr, "va: k_glv_pair: %d clusters of %d CTAs\n", e->grid / e->pair_cl, e->pair_cl);
             e->glv_blk = va_glv_pair_block_doubles(desc->stepper);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+            e->pair_seg = policy == VA_CKPT_RECOMPUTE;
+            if (e->pair_seg) {
+                // recompute policy: (t_n, x_n) of every accepted step in a per-CTA state store, stage blocks only for one segment
+                // (16 steps x 36.9 KB x 148 CTAs = 87 MB: L2-resident); VA_PAIR_SEG overrides the segment length
+                const int sl = getenv("VA_PAIR_SEG") ? atoi(getenv("VA_PAIR_SEG")) : 16;
+                e->pair_seg_len = sl < 1 ? 1 : sl;
+                e->slab_stride = (int64_t)(e->pair_seg_len + 1) * e->glv_blk;
+                e->xstore_stride = (int64_t)(e->cap + 1) * (8 + 256);
+            }
         }
         if (e->ring) {
             e->ctas_per_sm = 1;
@@ -760,8 +780,9 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
         // first wave: trajectory b = slot b, slab 0 (cluster-pair kernel: CTA 2b of pair b)
-        const double *base = e->slab.as<double>() + b * (e->pairk ? e->pair_cl : e->pair) * e->slab_stride;
-        const size_t pitch = (size_t)(e->family == FAM_GLV_WIDE || e->ring || e->pairk ? e->glv_blk
+        const double *base = e->pair_seg ? e->xstore.as<double>() + b * e->pair_cl * e->xstore_stride
+                                         : e->slab.as<double>() + b * (e->pairk ? e->pair_cl : e->pair) * e->slab_stride;
+        const size_t pitch = e->pair_seg ? (size_t)(8 + 256) * 8 : (size_t)(e->family == FAM_GLV_WIDE || e->ring || e->pairk ? e->glv_blk
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {

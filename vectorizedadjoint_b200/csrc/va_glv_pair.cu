@@ -233,7 +233,12 @@ __device__ __forceinline__ double product_cols(Pair<CL> &P, const double (&creg)
 
 // EXACT: a.n == N. Otherwise 64 < a.n < N species are padded with inert ones (x = r = 0, zero matrix rows and columns): the
 // parameter blocks keep their row stride a.n in global memory, the kernel's vectors and step blocks are N wide.
-template <class Tab, bool ADAPTIVE, int CL, bool EXACT>
+// SEG: recompute policy (north_star item 4; the reference's policy, detail/backpropagation.hpp:24-64). The forward sweep keeps
+// only (t_n, x_n) per accepted step in the CTA's state store; the reverse sweep walks the trajectory in segments of a.seg_len
+// steps, newest first: it re-integrates a segment from the stored states with dt = t_{n+1} - t_n (StateStorage::GetDt,
+// StateStorage.hpp:22), leaving the usual stage blocks in a slab of seg_len blocks, then runs phases 2 and 3 over that
+// segment. Six more products per step (18 instead of 12); checkpoint memory 8 (N + 8) B per step instead of 36.9 KB.
+template <class Tab, bool ADAPTIVE, int CL, bool EXACT, bool SEG>
 __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGlvWideArgs a)
 {
     constexpr int HR = Pair<CL>::HR, SR = Pair<CL>::SR;
@@ -287,6 +292,8 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
     }
     cluster_barrier(); // barriers initialised; the partner has started (its shared memory may be written from here on)
     double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
+    constexpr int XB = 8 + N; // state-store entry: [8-double header (t_n) | x_n]
+    double *const xstore = SEG ? a.xstore + (int64_t)blockIdx.x * a.xstore_stride : nullptr;
     double creg[CR];
     bool row_init = false; // summed mode: this pair's partial-sum row has been written
 
@@ -313,24 +320,40 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 bulk_g2s(reinterpret_cast<unsigned char *>(sc) + off, reinterpret_cast<const unsigned char *>(Aown) + off, TMA_PIECE, bar, pol);
         }
         // register rows, row layout: 8 rows per warp, 8 columns per lane and row
+        auto load_rows = [&]() {
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (EXACT) {
-                    const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
-                    creg[r * 8 + 2 * k] = t.x;
-                    creg[r * 8 + 2 * k + 1] = t.y;
-                } else {
-                    const int row = row0 + SR + warp * 8 + r, col = 64 * k + 2 * lane;
+                for (int k = 0; k < 4; ++k) {
+                    if (EXACT) {
+                        const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
+                        creg[r * 8 + 2 * k] = t.x;
+                        creg[r * 8 + 2 * k + 1] = t.y;
+                    } else {
+                        const int row = row0 + SR + warp * 8 + r, col = 64 * k + 2 * lane;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const bool in = row < n && col + e < n;
-                        const double v = __ldg(pb + n + (in ? (size_t)row * n + col + e : 0));
-                        creg[r * 8 + 2 * k + e] = in ? v : 0.0;
+                        for (int e = 0; e < 2; ++e) {
+                            const bool in = row < n && col + e < n;
+                            const double v = __ldg(pb + n + (in ? (size_t)row * n + col + e : 0));
+                            creg[r * 8 + 2 * k + e] = in ? v : 0.0;
+                        }
                     }
                 }
+        };
+        // register rows, column layout: creg[i] = A[own row SR + i][tid]
+        auto load_cols = [&]() {
+#pragma unroll
+            for (int i = 0; i < CR; ++i) {
+                if (EXACT) {
+                    creg[i] = __ldg(Ac + (size_t)i * N + tid);
+                } else {
+                    const bool in = live && row0 + SR + i < n;
+                    const double v = __ldg(pb + n + (in ? (size_t)(row0 + SR + i) * n + tid : 0));
+                    creg[i] = in ? v : 0.0;
+                }
             }
+        };
+        load_rows();
         rr[tid] = live ? __ldg(pb + tid) : 0.0;
         double x = live ? a.x0[b * n + tid] : 0.0;
         P.xin()[tid] = x;
@@ -351,9 +374,15 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             double *blk = slab + (int64_t)nck * BLK;
             if (fresh) {
                 if (nck >= a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
-                blk[OFF_X + tid] = x;
-                blk[OFF_G + tid] = g0;
-                if (tid == 0) blk[0] = t;
+                if (SEG) {
+                    double *xb = xstore + (int64_t)nck * XB;
+                    xb[8 + tid] = x;
+                    if (tid == 0) xb[0] = t;
+                } else {
+                    blk[OFF_X + tid] = x;
+                    blk[OFF_G + tid] = g0;
+                    if (tid == 0) blk[0] = t;
+                }
                 if (ADAPTIVE && va_less_with_sign(tf, t + dt, dt)) dt = tf - t;
                 trials = 0;
                 fresh = false;
@@ -366,11 +395,11 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                     if (Tab::a(m, j) != 0.0) acc = fma(Tab::a(m, j), K[j], acc);
                 const double xm = fma(dt, acc, x);
                 P.xin()[tid] = xm;
-                if (m < SADJ) blk[OFF_X + m * N + tid] = xm;
+                if (!SEG && m < SADJ) blk[OFF_X + m * N + tid] = xm;
                 __syncthreads();
                 const double gm = product_rows(P, rr, creg, tid);
                 K[m] = xm * gm;
-                if (m < SADJ) blk[OFF_G + m * N + tid] = gm;
+                if (!SEG && m < SADJ) blk[OFF_G + m * N + tid] = gm;
             }
             double xnew;
             {
@@ -439,7 +468,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             }
         }
         const int T = nck;
-        if (tid == 0) slab[(int64_t)T * BLK] = t;
+        if (tid == 0) {
+            if (SEG) xstore[(int64_t)T * XB] = t; // entry T carries the final time
+            else slab[(int64_t)T * BLK] = t;
+        }
         if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
         status = __syncthreads_or(status); // also: every slab store of the forward sweep is visible to the CTA
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
@@ -467,23 +499,48 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 }
                 continue;
             }
-            // ---- phase 2: state adjoint ----
-#pragma unroll
-            for (int i = 0; i < CR; ++i) { // column layout
-                if (EXACT) {
-                    creg[i] = __ldg(Ac + (size_t)i * N + tid);
-                } else {
-                    const bool in = live && row0 + SR + i < n;
-                    const double v = __ldg(pb + n + (in ? (size_t)(row0 + SR + i) * n + tid : 0));
-                    creg[i] = in ? v : 0.0;
-                }
-            }
             double lam = !live ? 0.0 : a.objective == VA_OBJ_SUM ? 1.0 : a.objective == VA_OBJ_HALF_NORM2 ? x : lam_io[tid];
             double rbar = 0.0;
             double t_hi = t_final;
+            // the trajectory is walked in segments [s0, s1) of steps, newest first (store-stages policy: one segment, all steps)
+            int s1 = T;
+            bool first_seg = true;
+            do {
+            const int s0 = SEG ? (s1 > a.seg_len ? s1 - a.seg_len : 0) : 0;
+            const int Tseg = s1 - s0;
+            if (SEG) {
+                // ---- re-integration of the segment from the stored states (rows of A in row layout) ----
+                if (o > 0 || !first_seg) load_rows(); // (the forward sweep left the row layout behind for the first segment of the first seed)
 #pragma unroll 1
-            for (int step = T - 1; step >= 0; --step) {
-                double *blk = slab + (int64_t)step * BLK;
+                for (int nn = s0; nn < s1; ++nn) {
+                    const double *xb = xstore + (int64_t)nn * XB;
+                    const double xn = xb[8 + tid], tn = xb[0], tn1 = xb[XB];
+                    const double dts = tn1 - tn;
+                    double *blk = slab + (int64_t)(nn - s0) * BLK;
+                    if (tid == 0) blk[0] = tn;
+                    double Kr[SADJ];
+#pragma unroll
+                    for (int m = 0; m < SADJ; ++m) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int j = 0; j < m; ++j)
+                            if (Tab::a(m, j) != 0.0) acc = fma(Tab::a(m, j), Kr[j], acc);
+                        const double xm = m == 0 ? xn : fma(dts, acc, xn);
+                        P.xin()[tid] = xm;
+                        blk[OFF_X + m * N + tid] = xm;
+                        __syncthreads();
+                        const double gm = product_rows(P, rr, creg, tid);
+                        Kr[m] = xm * gm;
+                        blk[OFF_G + m * N + tid] = gm;
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- phase 2: state adjoint (rows of A in column layout) ----
+            load_cols();
+#pragma unroll 1
+            for (int step = s1 - 1; step >= s0; --step) {
+                double *blk = slab + (int64_t)(step - s0) * BLK;
                 const double t_lo = blk[0];
                 const double dt_s = t_hi - t_lo;
                 t_hi = t_lo;
@@ -511,11 +568,6 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                         if (Tab::a(m - 1, k - 1) != 0.0) W[k] = fma(gx * Tab::a(m - 1, k - 1), dt_s, W[k]);
                 }
                 lam = W[0];
-            }
-            if (rank == 0 && live) {
-                lam_io[tid] = lam;
-                if (overwrite) gbar[tid] = rbar;
-                else atomicAdd(gbar + tid, rbar);
             }
             // every v block of this CTA's slab is written (generic proxy); the bulk copies below read them through the async proxy
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -546,10 +598,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                     for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
                 if (tid == 0) {
 #pragma unroll 1
-                    for (int k = 0; k < P3_STAGES && k < T; ++k) p3_issue(k, cb, p3q + (uint32_t)k);
+                    for (int k = 0; k < P3_STAGES && k < Tseg; ++k) p3_issue(k, cb, p3q + (uint32_t)k);
                 }
 #pragma unroll 1
-                for (int step = 0; step < T; ++step) {
+                for (int step = 0; step < Tseg; ++step) {
                     const int st = (int)(p3q % P3_STAGES);
                     mbar_wait_or_trap(bar + 3 + st, (p3q / P3_STAGES) & 1u);
                     const double *Vs = p3buf + (size_t)st * P3_STAGE_DOUBLES, *Xs = Vs + SADJ * N;
@@ -571,9 +623,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                             for (int c = 0; c < 8; ++c) acc[r][c] = fma(v8[r], x8[c], acc[r][c]);
                     }
                     __syncthreads(); // every thread is done with this stage
-                    if (tid == 0 && step + P3_STAGES < T) p3_issue(step + P3_STAGES, cb, p3q + (uint32_t)P3_STAGES);
+                    if (tid == 0 && step + P3_STAGES < Tseg) p3_issue(step + P3_STAGES, cb, p3q + (uint32_t)P3_STAGES);
                     ++p3q;
                 }
+                const bool ow = overwrite && first_seg;
                 // Abar tile out: plain stores on first use of the row, fire-and-forget reductions afterwards (one writer per
                 // address, program order: deterministic)
 #pragma unroll
@@ -583,7 +636,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                         const int row = 8 * ty + r, col = cb + 16 * q + 2 * tx;
                         double *dst = gbar + n + (size_t)row * n + col;
                         if (EXACT) {
-                            if (overwrite) {
+                            if (ow) {
                                 *reinterpret_cast<double2 *>(dst) = make_double2(acc[r][2 * q], acc[r][2 * q + 1]);
                             } else {
                                 atomicAdd(dst, acc[r][2 * q]);
@@ -593,11 +646,20 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
 #pragma unroll
                             for (int e = 0; e < 2; ++e)
                                 if (row < n && col + e < n) {
-                                    if (overwrite) dst[e] = acc[r][2 * q + e];
+                                    if (ow) dst[e] = acc[r][2 * q + e];
                                     else atomicAdd(dst + e, acc[r][2 * q + e]);
                                 }
                         }
                     }
+            }
+            __syncthreads(); // the slab is free for the next segment
+            first_seg = false;
+            s1 = s0;
+            } while (s1 > 0);
+            if (rank == 0 && live) {
+                lam_io[tid] = lam;
+                if (overwrite) gbar[tid] = rbar;
+                else atomicAdd(gbar + tid, rbar);
             }
             row_init = true;
         }
@@ -619,9 +681,13 @@ template <class Tab, bool ADAPTIVE, int CL>
 cudaError_t configure(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &at, int grid, cudaStream_t st)
 {
     const size_t smem = smem_bytes<Tab, ADAPTIVE, CL>();
-    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_glv_pair<Tab, ADAPTIVE, CL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -643,8 +709,13 @@ cudaError_t launch2(const VaGlvWideArgs &a, cudaStream_t st)
     cudaLaunchAttribute at;
     cudaError_t e = configure<Tab, ADAPTIVE, CL>(cfg, at, a.grid, st);
     if (e != cudaSuccess) return e;
-    return a.n == N ? cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, true>, a)
-                    : cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, false>, a);
+    if (a.recompute) {
+        if (!a.xstore || a.seg_len < 1) return cudaErrorInvalidValue;
+        return a.n == N ? cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, true, true>, a)
+                        : cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, false, true>, a);
+    }
+    return a.n == N ? cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, true, false>, a)
+                    : cudaLaunchKernelEx(&cfg, k_glv_pair<Tab, ADAPTIVE, CL, false, false>, a);
 }
 template <class Tab, bool ADAPTIVE>
 cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st)
@@ -658,7 +729,7 @@ cudaError_t max_clusters2(int sm_count, int *n)
     cudaLaunchAttribute at;
     cudaError_t e = configure<Tab, ADAPTIVE, CL>(cfg, at, sm_count / CL * CL, nullptr);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveClusters(n, k_glv_pair<Tab, ADAPTIVE, CL, true>, &cfg);
+    return cudaOccupancyMaxActiveClusters(n, k_glv_pair<Tab, ADAPTIVE, CL, true, false>, &cfg);
 }
 template <class Tab, bool ADAPTIVE>
 cudaError_t max_clusters(int cl, int sm_count, int *n)
