@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--reduce", default="sum", choices=["sum", "none"])
     ap.add_argument("--workload", default="glv64", choices=sorted(WORKLOADS), help="glv64 = the headline contract line")
     ap.add_argument("--species", type=int, default=0, help="with --workload glv256: any other species count (same tolerances; not a BASELINE config)")
+    ap.add_argument("--ckpt-policy", default="auto", choices=["auto", "recompute", "store"], help="side workloads: checkpoint policy of the engine")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="parameter sets per reference-arm step (0 = auto)")
@@ -244,7 +245,8 @@ def side_workload(args):
     x_final, lam = torch.empty(B, n, **f64), torch.empty(B, 1, n, **f64)
     mu = torch.empty((1, npar) if red == va.REDUCE_SUM else (B, 1, npar), **f64)
     n_acc, n_rej, status = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3))
-    eng = va.Engine(system, n, stepper, adaptive, tol, tol, device=local, max_steps=max_steps)
+    eng = va.Engine(system, n, stepper, adaptive, tol, tol, device=local, max_steps=max_steps,
+                    ckpt_policy={"auto": va.CKPT_AUTO, "recompute": va.CKPT_RECOMPUTE, "store": va.CKPT_STORE_STAGES}[args.ckpt_policy])
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
 
@@ -281,7 +283,8 @@ def side_workload(args):
     line = {"metric": f"fwd+adjoint gradients/sec, {args.workload} batch {Btot}", "value": Btot / (ms * 1e-3), "unit": "gradients/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "batch_total": Btot, "reduce": args.reduce, "parallelism": f"batch sharded over {world} GPU(s)"},
+            "config": {"workload": desc, "batch_total": Btot, "reduce": args.reduce, "parallelism": f"batch sharded over {world} GPU(s)",
+                       "ckpt_policy": {va.CKPT_RECOMPUTE: "recompute", va.CKPT_STORE_STAGES: "store_stages"}.get(eng.info()["ckpt_policy"], "auto")},
             "gpu_launches": info["kernel_launches"] - l0,
             "mean_accepted_steps": T / max(B, 1), "mean_rejected": R / max(B, 1), "max_accepted_steps": int(n_acc.max()) if B else 0,
             "failed_trajectories": int((status != 0).sum()), "clocks": clk}

@@ -231,6 +231,46 @@ __device__ __forceinline__ double product_cols(Pair<CL> &P, const double (&creg)
     return y;
 }
 
+// register rows of the CTA's matrix part, row layout: warp w holds own rows SR + 8 w + r, lane l their columns {64k + 2l, 64k + 2l + 1}
+// (always inlined: the register array must never be addressed through a pointer)
+template <bool EXACT, int SR>
+__device__ __forceinline__ void load_rows_f(double (&creg)[CR], const double *Ac, const double *pb, int n, int row0, int warp, int lane)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (EXACT) {
+                const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
+                creg[r * 8 + 2 * k] = t.x;
+                creg[r * 8 + 2 * k + 1] = t.y;
+            } else {
+                const int row = row0 + SR + warp * 8 + r, col = 64 * k + 2 * lane;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool in = row < n && col + e < n;
+                    const double v = __ldg(pb + n + (in ? (size_t)row * n + col + e : 0)); // padded entries read a valid address and discard it
+                    creg[r * 8 + 2 * k + e] = in ? v : 0.0;
+                }
+            }
+        }
+}
+// ... column layout: creg[i] = A[own row SR + i][tid]
+template <bool EXACT, int SR>
+__device__ __forceinline__ void load_cols_f(double (&creg)[CR], const double *Ac, const double *pb, int n, int row0, int tid, bool live)
+{
+#pragma unroll
+    for (int i = 0; i < CR; ++i) {
+        if (EXACT) {
+            creg[i] = __ldg(Ac + (size_t)i * N + tid);
+        } else {
+            const bool in = live && row0 + SR + i < n;
+            const double v = __ldg(pb + n + (in ? (size_t)(row0 + SR + i) * n + tid : 0));
+            creg[i] = in ? v : 0.0;
+        }
+    }
+}
+
 // EXACT: a.n == N. Otherwise 64 < a.n < N species are padded with inert ones (x = r = 0, zero matrix rows and columns): the
 // parameter blocks keep their row stride a.n in global memory, the kernel's vectors and step blocks are N wide.
 // SEG: recompute policy (north_star item 4; the reference's policy, detail/backpropagation.hpp:24-64). The forward sweep keeps
@@ -319,40 +359,8 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             for (uint32_t off = 0; off < (uint32_t)(SR * N * 8); off += TMA_PIECE)
                 bulk_g2s(reinterpret_cast<unsigned char *>(sc) + off, reinterpret_cast<const unsigned char *>(Aown) + off, TMA_PIECE, bar, pol);
         }
-        // register rows, row layout: 8 rows per warp, 8 columns per lane and row
-        auto load_rows = [&]() {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (EXACT) {
-                        const double2 t = __ldg(reinterpret_cast<const double2 *>(Ac + (size_t)(warp * 8 + r) * N + 64 * k + 2 * lane));
-                        creg[r * 8 + 2 * k] = t.x;
-                        creg[r * 8 + 2 * k + 1] = t.y;
-                    } else {
-                        const int row = row0 + SR + warp * 8 + r, col = 64 * k + 2 * lane;
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const bool in = row < n && col + e < n;
-                            const double v = __ldg(pb + n + (in ? (size_t)row * n + col + e : 0));
-                            creg[r * 8 + 2 * k + e] = in ? v : 0.0;
-                        }
-                    }
-                }
-        };
-        // register rows, column layout: creg[i] = A[own row SR + i][tid]
-        auto load_cols = [&]() {
-#pragma unroll
-            for (int i = 0; i < CR; ++i) {
-                if (EXACT) {
-                    creg[i] = __ldg(Ac + (size_t)i * N + tid);
-                } else {
-                    const bool in = live && row0 + SR + i < n;
-                    const double v = __ldg(pb + n + (in ? (size_t)(row0 + SR + i) * n + tid : 0));
-                    creg[i] = in ? v : 0.0;
-                }
-            }
-        };
+        auto load_rows = [&]() { load_rows_f<EXACT, SR>(creg, Ac, pb, n, row0, warp, lane); };
+        auto load_cols = [&]() { load_cols_f<EXACT, SR>(creg, Ac, pb, n, row0, tid, live); };
         load_rows();
         rr[tid] = live ? __ldg(pb + tid) : 0.0;
         double x = live ? a.x0[b * n + tid] : 0.0;
@@ -510,7 +518,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             const int Tseg = s1 - s0;
             if (SEG) {
                 // ---- re-integration of the segment from the stored states (rows of A in row layout) ----
-                if (o > 0 || !first_seg) load_rows(); // (the forward sweep left the row layout behind for the first segment of the first seed)
+                // Unconditional reload (also for the first segment of the first seed, where the forward sweep's copy would do): a
+                // conditional one keeps the register rows live across phase 3 of the previous segment, next to its 128 accumulator
+                // registers -- ptxas then spills a third of the rows for the whole kernel (1.2 KB of spill stores, 7 KB of loads).
+                load_rows();
 #pragma unroll 1
                 for (int nn = s0; nn < s1; ++nn) {
                     const double *xb = xstore + (int64_t)nn * XB;
@@ -572,6 +583,13 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             // every v block of this CTA's slab is written (generic proxy); the bulk copies below read them through the async proxy
             asm volatile("fence.proxy.async;" ::: "memory");
             __syncthreads();
+            if (SEG) {
+                // phase 3 needs every register for its accumulators: park the three values that outlive it (each thread reads back
+                // what it wrote; xs and yp are idle until the next product, which comes after the reload)
+                xs[tid] = lam;
+                xs[N + tid] = rbar;
+                yp[tid] = t_hi;
+            }
 
             // ---- phase 3: Abar = sum_k v_k X_k^T; this CTA takes columns [128 rank, 128 rank + 128) in two 64-column passes ----
             // thread (ty, tx): rows 8 ty + r, columns cb + 16 c + 2 tx + e  (r < 8, c < 4, e < 2). The operands of a step
@@ -653,6 +671,11 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                     }
             }
             __syncthreads(); // the slab is free for the next segment
+            if (SEG) {
+                lam = xs[tid];
+                rbar = xs[N + tid];
+                t_hi = yp[tid];
+            }
             first_seg = false;
             s1 = s0;
             } while (s1 > 0);
