@@ -186,32 +186,67 @@ __device__ __forceinline__ double product_rows(Pair<CL> &P, const double *rr, co
     return g;
 }
 
-// returns (A^T v)_tid for v = P.xin(), visible to all threads of this CTA. Register rows in column layout:
-// creg[i] = A[own row SR + i][tid].
+// returns (A^T v)_tid for v = P.xin(), visible to all threads of this CTA. Same register/shared-memory row layout as product_rows
+// ("transposed row product"): warp w forms, for the 8 columns of each lane, the partial sums over its 16 rows (8 in registers, 8
+// in shared memory) -- the v operands are 16 warp-uniform values instead of the 128 every thread would need as the owner of a
+// whole column (an LDS.128 costs four LSU wavefronts even when all lanes read the same address: the column-owner version spent
+// 2/3 of its LSU time on those broadcasts and was LSU-bound at 384 wavefronts per warp and product; this one needs 176) -- then
+// the 8 warps' partial rows are summed through shared memory (wpart: [8][N] doubles, free between products).
 template <int CL>
-__device__ __forceinline__ double product_cols(Pair<CL> &P, const double (&creg)[CR], int tid)
+__device__ __forceinline__ double product_cols(Pair<CL> &P, const double (&creg)[CR], double *wpart, int tid)
 {
     constexpr int HR = Pair<CL>::HR, SR = Pair<CL>::SR;
+    const int lane = tid & 31, warp = tid >> 5;
     const uint32_t pp = P.q & 1u, par = (P.q >> 1) & 1u;
     if (tid == 0) mbar_expect_tx(&P.xbar[pp], (CL - 1) * N * 8); // the peers' partial sums for all columns
-    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const double *vo = P.xin() + (int)P.rank * HR; // v of the own rows
-    if (SR > 0) {
-        const double *col = P.sc + tid;
+    double pc[8];                                  // pc[2k + e]: column 64 k + 2 lane + e
+    {
+        double vr[8];
 #pragma unroll
-        for (int i = 0; i < SR; i += 2) { // shared-memory rows first: their loads overlap the register rows' arithmetic
-            const double2 t = *reinterpret_cast<const double2 *>(vo + i);
-            acc[i & 7] = fma(col[(size_t)i * N], t.x, acc[i & 7]);
-            acc[(i + 1) & 7] = fma(col[(size_t)(i + 1) * N], t.y, acc[(i + 1) & 7]);
+        for (int i = 0; i < 4; ++i) {
+            const double2 t = *reinterpret_cast<const double2 *>(vo + SR + 8 * warp + 2 * i);
+            vr[2 * i] = t.x;
+            vr[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pc[k] = creg[k] * vr[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pc[k] = fma(creg[r * 8 + k], vr[r], pc[k]);
+    }
+    if (SR > 0) {
+        double vs[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 t = *reinterpret_cast<const double2 *>(vo + 8 * warp + 2 * i);
+            vs[2 * i] = t.x;
+            vs[2 * i + 1] = t.y;
+        }
+        const double *rowp = P.sc + (size_t)(8 * warp) * N + 2 * lane;
+#pragma unroll
+        for (int r0 = 0; r0 < 8; r0 += 4) { // four rows (16 LDS.128) in flight
+            double2 t[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[r][k] = *reinterpret_cast<const double2 *>(rowp + (r0 + r) * N + 64 * k);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pc[2 * k] = fma(t[r][k].x, vs[r0 + r], pc[2 * k]);
+                    pc[2 * k + 1] = fma(t[r][k].y, vs[r0 + r], pc[2 * k + 1]);
+                }
         }
     }
 #pragma unroll
-    for (int i = 0; i < CR; i += 2) {
-        const double2 t = *reinterpret_cast<const double2 *>(vo + SR + i);
-        acc[i & 7] = fma(creg[i], t.x, acc[i & 7]);
-        acc[(i + 1) & 7] = fma(creg[i + 1], t.y, acc[(i + 1) & 7]);
-    }
-    const double part = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(wpart + warp * N + 64 * k + 2 * lane) = make_double2(pc[2 * k], pc[2 * k + 1]);
+    __syncthreads();
+    double part = wpart[tid];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) part += wpart[w * N + tid];
 #pragma unroll
     for (int d = 0; d < CL - 1; ++d) st_async_f64(P.yp_remote[d] + ((pp * CL + P.rank) * N + tid) * 8u, part, P.xbar_remote[d] + pp * 8u);
     mbar_wait_or_trap(&P.xbar[pp], par);
@@ -255,22 +290,6 @@ __device__ __forceinline__ void load_rows_f(double (&creg)[CR], const double *Ac
             }
         }
 }
-// ... column layout: creg[i] = A[own row SR + i][tid]
-template <bool EXACT, int SR>
-__device__ __forceinline__ void load_cols_f(double (&creg)[CR], const double *Ac, const double *pb, int n, int row0, int tid, bool live)
-{
-#pragma unroll
-    for (int i = 0; i < CR; ++i) {
-        if (EXACT) {
-            creg[i] = __ldg(Ac + (size_t)i * N + tid);
-        } else {
-            const bool in = live && row0 + SR + i < n;
-            const double v = __ldg(pb + n + (in ? (size_t)(row0 + SR + i) * n + tid : 0));
-            creg[i] = in ? v : 0.0;
-        }
-    }
-}
-
 // EXACT: a.n == N. Otherwise 64 < a.n < N species are padded with inert ones (x = r = 0, zero matrix rows and columns): the
 // parameter blocks keep their row stride a.n in global memory, the kernel's vectors and step blocks are N wide.
 // SEG: recompute policy (north_star item 4; the reference's policy, detail/backpropagation.hpp:24-64). The forward sweep keeps
@@ -360,7 +379,6 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 bulk_g2s(reinterpret_cast<unsigned char *>(sc) + off, reinterpret_cast<const unsigned char *>(Aown) + off, TMA_PIECE, bar, pol);
         }
         auto load_rows = [&]() { load_rows_f<EXACT, SR>(creg, Ac, pb, n, row0, warp, lane); };
-        auto load_cols = [&]() { load_cols_f<EXACT, SR>(creg, Ac, pb, n, row0, tid, live); };
         load_rows();
         rr[tid] = live ? __ldg(pb + tid) : 0.0;
         double x = live ? a.x0[b * n + tid] : 0.0;
@@ -516,12 +534,12 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             do {
             const int s0 = SEG ? (s1 > a.seg_len ? s1 - a.seg_len : 0) : 0;
             const int Tseg = s1 - s0;
+            // The register rows are reloaded at the top of EVERY segment (and seed), although they never change: an unconditional
+            // reload ends their live range before phase 3, whose 128 accumulator registers cannot coexist with them (a conditional or
+            // missing reload makes ptxas spill a third of the rows for the whole kernel).
+            load_rows();
             if (SEG) {
-                // ---- re-integration of the segment from the stored states (rows of A in row layout) ----
-                // Unconditional reload (also for the first segment of the first seed, where the forward sweep's copy would do): a
-                // conditional one keeps the register rows live across phase 3 of the previous segment, next to its 128 accumulator
-                // registers -- ptxas then spills a third of the rows for the whole kernel (1.2 KB of spill stores, 7 KB of loads).
-                load_rows();
+                // ---- re-integration of the segment from the stored states ----
 #pragma unroll 1
                 for (int nn = s0; nn < s1; ++nn) {
                     const double *xb = xstore + (int64_t)nn * XB;
@@ -547,8 +565,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                 }
                 __syncthreads();
             }
-            // ---- phase 2: state adjoint (rows of A in column layout) ----
-            load_cols();
+            // ---- phase 2: state adjoint (transposed products with the same row layout) ----
 #pragma unroll 1
             for (int step = s1 - 1; step >= s0; --step) {
                 double *blk = slab + (int64_t)(step - s0) * BLK;
@@ -571,7 +588,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                     blk[OFF_V + (m - 1) * N + tid] = v;
                     rbar += v;
                     __syncthreads();
-                    const double atv = product_cols(P, creg, tid);
+                    const double atv = product_cols(P, creg, p3buf, tid);
                     const double gx = fma(W[m], Gr[m - 1], atv);
                     W[0] += gx;
 #pragma unroll
