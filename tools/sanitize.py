@@ -27,9 +27,9 @@ for N, stepper, adaptive, tol, n_out, B in [(64, va.RK_CK54, True, 1e-6, 1, 9), 
     assert (r["status"] == 0).all()
     print(N, "family", info["kernel_family"], info["kernel_name"], "threads", info["threads_per_cta"], "steps", r["n_accept"].tolist(), flush=True)
 # 256 species: cluster-pair kernel (DSMEM exchange, TMA loads), ring-streamed kernel, plain streamed kernel
-for env, B in [({}, 3), ({"VA_TEST_POLICY": "2", "VA_PAIR_SEG": "3"}, 2), ({"VA_GLV_NO_PAIR": "1", "VA_TEST_POLICY": "0"}, 2), ({"VA_GLV_NO_RING": "1"}, 1)]:
-    os.environ.update(env)
-    policy = int(os.environ.get("VA_TEST_POLICY", "0"))  # 2 = recompute (cluster kernel: state store + segment re-integration)
+for env, policy, B in [({}, va.CKPT_STORE_STAGES, 3), ({"VA_PAIR_SEG": "3"}, va.CKPT_RECOMPUTE, 2), ({"VA_GLV_NO_PAIR": "1"}, va.CKPT_AUTO, 2),
+                       ({"VA_GLV_NO_RING": "1"}, va.CKPT_AUTO, 1)]:
+    os.environ.update(env)  # recompute on the cluster kernel = state store + segment re-integration (3 steps per segment here)
     p = oracle.synth_params(oracle.SYS_GLV, 256, 5, 0, B)
     x0 = oracle.synth_x0(oracle.SYS_GLV, 256, p)
     seeds = np.random.default_rng(0).standard_normal((B, 2, 256))
