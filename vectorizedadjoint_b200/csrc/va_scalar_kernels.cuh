@@ -316,8 +316,11 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
     }
 }
 
+#ifndef VA_SCALAR_FWD_MINB
+#define VA_SCALAR_FWD_MINB 1 // resident CTAs per SM the forward kernel of the <= 7-stage steppers is sized for (experiment knob)
+#endif
 template <class Sys, int S, bool FSAL, bool ADAPTIVE>
-__global__ void __launch_bounds__(128) k_scalar_forward(const __grid_constant__ VaScalarArgs a)
+__global__ void __launch_bounds__(128, (S <= 7 ? VA_SCALAR_FWD_MINB : 1)) k_scalar_forward(const __grid_constant__ VaScalarArgs a)
 {
     scalar_forward_body<Sys, S, FSAL, ADAPTIVE>(a);
 }
