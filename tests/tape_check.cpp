@@ -59,7 +59,20 @@ struct Pendulum {
     }
 };
 
-int main()
+// every elementary function and the comparison / select surface (AADC idouble.h:660-741, ibool.h:19-28)
+struct Zoo {
+    template <class T> void operator()(const std::vector<T> &x, std::vector<T> &d, const std::vector<T> &p, const T t) const
+    {
+        using namespace std;
+        using va::iIf;
+        d[0] = tan(x[0]) + asin(x[1] * 0.5) - acos(p[0] * x[0]) + atan(x[2] * p[1]) + sinh(x[1]) * cosh(x[0]);
+        d[1] = log10(2.0 + x[0] * x[0]) + log2(1.5 + p[1] * p[1]) + exp2(x[2] * 0.3) + cbrt(1.0 + x[1] * x[1]) + erf(p[0] * x[2]) + fabs(x[0] - 0.9);
+        d[2] = atan2(x[0] + p[0], 1.0 + x[1] * x[1]) + fmod(3.7 * x[2] + p[1], 1.3) + fmin(x[0] * x[1], p[0]) + fmax(x[2], x[1] * p[1]) +
+               iIf(x[0] * p[1] < x[1] + t, x[0] * x[0], -x[1]) + iIf(x[2] >= p[0], p[1] * x[2], x[2] * x[2] * t);
+    }
+};
+
+int main(int argc, char **argv)
 {
     int fails = 0;
     auto expect = [&](const char *name, int got, int want) {
@@ -91,6 +104,30 @@ int main()
         fails += rc != VA_OK;
     }
     fails += va_tape_compile_check("struct VaUserSys { this is not CUDA };", VA_RK_RK4, log, sizeof(log)) != VA_E_NVRTC;
+    // the wider operation set: tape evaluation == direct evaluation; the functor compiles under NVRTC; its generated source is
+    // written out for the host-side derivative check of tests/test_dropin_cpu.py
+    {
+        va::Tape tz = va::record(Zoo(), 3, 2);
+        fails += va::identify(tz) != va::SYS_TAPE;
+        std::vector<double> xz = {0.31, 0.44, 0.52}, pz = {0.8, 0.6}, fz(3), gz(3);
+        tz.eval(xz.data(), pz.data(), 0.25, fz.data(), work);
+        Zoo()(xz, gz, pz, 0.25);
+        for (int i = 0; i < 3; ++i) fails += !(std::fabs(fz[i] - gz[i]) <= 1e-15 * std::fabs(gz[i]));
+        // the other branch of both selects
+        std::vector<double> xy = {0.95, 0.1, 0.85};
+        tz.eval(xy.data(), pz.data(), 0.25, fz.data(), work);
+        Zoo()(xy, gz, pz, 0.25);
+        for (int i = 0; i < 3; ++i) fails += !(std::fabs(fz[i] - gz[i]) <= 1e-15 * std::fabs(gz[i]));
+        const std::string zoo = tz.cuda_source("VaUserSys");
+        const int rc = va_tape_compile_check(zoo.c_str(), VA_RK_DOPRI5, log, sizeof(log));
+        std::printf("nvrtc zoo: rc %d %s\n", rc, rc ? va_last_error() : "");
+        fails += rc != VA_OK;
+        if (argc > 1) {
+            FILE *fo = std::fopen(argv[1], "w");
+            std::fputs(zoo.c_str(), fo);
+            std::fclose(fo);
+        }
+    }
     // Driver surface without a device: preconditions are reported on stdout, the call returns (reference behaviour)
     vectorizedadjoint::Driver driver(2, 1, 1);
     std::vector<double> mu = {0.1};

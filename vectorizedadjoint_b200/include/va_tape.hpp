@@ -19,13 +19,20 @@
 
 namespace va {
 
+// The operation set follows the surface of AADC's active scalar (reference aadc/include/aadc/idouble.h:242-631 arithmetic,
+// :660-741 elementary functions; ibool.h:19-28 comparisons and iIf).
 enum OpCode : uint8_t { OP_INPUT_X, OP_INPUT_P, OP_INPUT_T, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP,
-                        OP_LOG, OP_SQRT, OP_TANH, OP_POW };
+                        OP_LOG, OP_SQRT, OP_TANH, OP_POW,
+                        OP_TAN, OP_ASIN, OP_ACOS, OP_ATAN, OP_SINH, OP_COSH, OP_LOG10, OP_LOG2, OP_EXP2, OP_CBRT, OP_ERF, OP_FABS,
+                        OP_ATAN2, OP_FMOD, OP_FMIN, OP_FMAX,
+                        OP_LT, OP_LE, OP_GT, OP_GE, // comparisons: value 1.0 / 0.0, no derivative
+                        OP_SELECT };                // s ? a : b  (iIf)
 
 struct Node {
     OpCode op;
     int32_t a, b;   // operand node ids (or input index for OP_INPUT_*)
     double c;       // constant value (OP_CONST)
+    int32_t s = -1; // OP_SELECT: node id of the condition
 };
 
 class Tape
@@ -65,6 +72,27 @@ class Tape
             case OP_SQRT: v = std::sqrt(work[n.a]); break;
             case OP_TANH: v = std::tanh(work[n.a]); break;
             case OP_POW: v = std::pow(work[n.a], work[n.b]); break;
+            case OP_TAN: v = std::tan(work[n.a]); break;
+            case OP_ASIN: v = std::asin(work[n.a]); break;
+            case OP_ACOS: v = std::acos(work[n.a]); break;
+            case OP_ATAN: v = std::atan(work[n.a]); break;
+            case OP_SINH: v = std::sinh(work[n.a]); break;
+            case OP_COSH: v = std::cosh(work[n.a]); break;
+            case OP_LOG10: v = std::log10(work[n.a]); break;
+            case OP_LOG2: v = std::log2(work[n.a]); break;
+            case OP_EXP2: v = std::exp2(work[n.a]); break;
+            case OP_CBRT: v = std::cbrt(work[n.a]); break;
+            case OP_ERF: v = std::erf(work[n.a]); break;
+            case OP_FABS: v = std::fabs(work[n.a]); break;
+            case OP_ATAN2: v = std::atan2(work[n.a], work[n.b]); break;
+            case OP_FMOD: v = std::fmod(work[n.a], work[n.b]); break;
+            case OP_FMIN: v = work[n.a] < work[n.b] ? work[n.a] : work[n.b]; break;
+            case OP_FMAX: v = work[n.a] > work[n.b] ? work[n.a] : work[n.b]; break;
+            case OP_LT: v = work[n.a] < work[n.b] ? 1.0 : 0.0; break;
+            case OP_LE: v = work[n.a] <= work[n.b] ? 1.0 : 0.0; break;
+            case OP_GT: v = work[n.a] > work[n.b] ? 1.0 : 0.0; break;
+            case OP_GE: v = work[n.a] >= work[n.b] ? 1.0 : 0.0; break;
+            case OP_SELECT: v = work[n.s] != 0.0 ? work[n.a] : work[n.b]; break;
             }
             work[k] = v;
         }
@@ -145,11 +173,64 @@ VA_TAPE_UNARY(exp, OP_EXP)
 VA_TAPE_UNARY(log, OP_LOG)
 VA_TAPE_UNARY(sqrt, OP_SQRT)
 VA_TAPE_UNARY(tanh, OP_TANH)
+VA_TAPE_UNARY(tan, OP_TAN)
+VA_TAPE_UNARY(asin, OP_ASIN)
+VA_TAPE_UNARY(acos, OP_ACOS)
+VA_TAPE_UNARY(atan, OP_ATAN)
+VA_TAPE_UNARY(sinh, OP_SINH)
+VA_TAPE_UNARY(cosh, OP_COSH)
+VA_TAPE_UNARY(log10, OP_LOG10)
+VA_TAPE_UNARY(log2, OP_LOG2)
+VA_TAPE_UNARY(exp2, OP_EXP2)
+VA_TAPE_UNARY(cbrt, OP_CBRT)
+VA_TAPE_UNARY(erf, OP_ERF)
+VA_TAPE_UNARY(fabs, OP_FABS)
 #undef VA_TAPE_UNARY
-inline adouble pow(const adouble &a, const adouble &b)
+inline adouble abs(const adouble &a) { return fabs(a); }
+#define VA_TAPE_BINARY(FN, OP, EXPR)                                                                   \
+    inline adouble FN(const adouble &a, const adouble &b)                                              \
+    {                                                                                                  \
+        return adouble::rec(a, b) ? adouble::make(OP, EXPR, a.id(), b.id()) : adouble(EXPR);           \
+    }
+VA_TAPE_BINARY(pow, OP_POW, std::pow(a.val, b.val))
+VA_TAPE_BINARY(atan2, OP_ATAN2, std::atan2(a.val, b.val))
+VA_TAPE_BINARY(fmod, OP_FMOD, std::fmod(a.val, b.val))
+VA_TAPE_BINARY(fmin, OP_FMIN, (a.val < b.val ? a.val : b.val))
+VA_TAPE_BINARY(fmax, OP_FMAX, (a.val > b.val ? a.val : b.val))
+#undef VA_TAPE_BINARY
+inline adouble min(const adouble &a, const adouble &b) { return fmin(a, b); }
+inline adouble max(const adouble &a, const adouble &b) { return fmax(a, b); }
+
+// Recorded comparison (AADC's ibool): it does NOT convert to bool -- a branch on an active value would be frozen into the
+// tape at its recording-time outcome -- and is consumed by iIf(condition, a, b), which records a select.
+class abool
 {
-    return adouble::rec(a, b) ? adouble::make(OP_POW, std::pow(a.val, b.val), a.id(), b.id()) : adouble(std::pow(a.val, b.val));
+  public:
+    bool val = false;
+    int32_t node = -1;
+    abool() = default;
+    abool(bool v) : val(v) {}
+};
+#define VA_TAPE_COMPARE(SYM, OP)                                                                       \
+    inline abool operator SYM(const adouble &a, const adouble &b)                                      \
+    {                                                                                                  \
+        abool r(a.val SYM b.val);                                                                      \
+        if (adouble::rec(a, b)) r.node = adouble::make(OP, r.val ? 1.0 : 0.0, a.id(), b.id()).node;    \
+        return r;                                                                                      \
+    }
+VA_TAPE_COMPARE(<, OP_LT)
+VA_TAPE_COMPARE(<=, OP_LE)
+VA_TAPE_COMPARE(>, OP_GT)
+VA_TAPE_COMPARE(>=, OP_GE)
+#undef VA_TAPE_COMPARE
+inline adouble iIf(const abool &c, const adouble &a, const adouble &b)
+{
+    if (c.node < 0) return c.val ? a : b; // condition on passive values: an ordinary branch
+    adouble r = adouble::make(OP_SELECT, c.val ? a.val : b.val, a.id(), b.id());
+    active_tape()->nodes[(size_t)r.node].s = c.node;
+    return r;
 }
+inline double iIf(bool c, double a, double b) { return c ? a : b; } // the same functor body instantiated with T = double
 
 // Record system(x, dxdt, p, t) once. Mirrors AadData::Record (reference lib/include/AadData.hpp:124-171).
 template <class System>
@@ -252,6 +333,27 @@ inline std::string Tape::cuda_source(const std::string &name) const
             case OP_SQRT: o << "sqrt(" << v(n.a) << ")"; break;
             case OP_TANH: o << "tanh(" << v(n.a) << ")"; break;
             case OP_POW: o << "pow(" << v(n.a) << ", " << v(n.b) << ")"; break;
+            case OP_TAN: o << "tan(" << v(n.a) << ")"; break;
+            case OP_ASIN: o << "asin(" << v(n.a) << ")"; break;
+            case OP_ACOS: o << "acos(" << v(n.a) << ")"; break;
+            case OP_ATAN: o << "atan(" << v(n.a) << ")"; break;
+            case OP_SINH: o << "sinh(" << v(n.a) << ")"; break;
+            case OP_COSH: o << "cosh(" << v(n.a) << ")"; break;
+            case OP_LOG10: o << "log10(" << v(n.a) << ")"; break;
+            case OP_LOG2: o << "log2(" << v(n.a) << ")"; break;
+            case OP_EXP2: o << "exp2(" << v(n.a) << ")"; break;
+            case OP_CBRT: o << "cbrt(" << v(n.a) << ")"; break;
+            case OP_ERF: o << "erf(" << v(n.a) << ")"; break;
+            case OP_FABS: o << "fabs(" << v(n.a) << ")"; break;
+            case OP_ATAN2: o << "atan2(" << v(n.a) << ", " << v(n.b) << ")"; break;
+            case OP_FMOD: o << "fmod(" << v(n.a) << ", " << v(n.b) << ")"; break;
+            case OP_FMIN: o << "(" << v(n.a) << " < " << v(n.b) << " ? " << v(n.a) << " : " << v(n.b) << ")"; break;
+            case OP_FMAX: o << "(" << v(n.a) << " > " << v(n.b) << " ? " << v(n.a) << " : " << v(n.b) << ")"; break;
+            case OP_LT: o << "(" << v(n.a) << " < " << v(n.b) << " ? 1.0 : 0.0)"; break;
+            case OP_LE: o << "(" << v(n.a) << " <= " << v(n.b) << " ? 1.0 : 0.0)"; break;
+            case OP_GT: o << "(" << v(n.a) << " > " << v(n.b) << " ? 1.0 : 0.0)"; break;
+            case OP_GE: o << "(" << v(n.a) << " >= " << v(n.b) << " ? 1.0 : 0.0)"; break;
+            case OP_SELECT: o << "(" << v(n.s) << " != 0.0 ? " << v(n.a) << " : " << v(n.b) << ")"; break;
             }
             o << ";\n";
         }
@@ -282,6 +384,26 @@ inline std::string Tape::cuda_source(const std::string &name) const
             o << "    " << d(n.a) << " += " << d(k) << " * " << v(n.b) << " * pow(" << v(n.a) << ", " << v(n.b) << " - 1.0); " << d(n.b)
               << " += " << d(k) << " * " << v(k) << " * log(" << v(n.a) << ");\n";
             break;
+        case OP_TAN: o << "    " << d(n.a) << " += " << d(k) << " * (1.0 + " << v(k) << " * " << v(k) << ");\n"; break;
+        case OP_ASIN: o << "    " << d(n.a) << " += " << d(k) << " / sqrt(1.0 - " << v(n.a) << " * " << v(n.a) << ");\n"; break;
+        case OP_ACOS: o << "    " << d(n.a) << " -= " << d(k) << " / sqrt(1.0 - " << v(n.a) << " * " << v(n.a) << ");\n"; break;
+        case OP_ATAN: o << "    " << d(n.a) << " += " << d(k) << " / (1.0 + " << v(n.a) << " * " << v(n.a) << ");\n"; break;
+        case OP_SINH: o << "    " << d(n.a) << " += " << d(k) << " * cosh(" << v(n.a) << ");\n"; break;
+        case OP_COSH: o << "    " << d(n.a) << " += " << d(k) << " * sinh(" << v(n.a) << ");\n"; break;
+        case OP_LOG10: o << "    " << d(n.a) << " += " << d(k) << " / (" << v(n.a) << " * 2.302585092994046);\n"; break;
+        case OP_LOG2: o << "    " << d(n.a) << " += " << d(k) << " / (" << v(n.a) << " * 0.6931471805599453);\n"; break;
+        case OP_EXP2: o << "    " << d(n.a) << " += " << d(k) << " * " << v(k) << " * 0.6931471805599453;\n"; break;
+        case OP_CBRT: o << "    " << d(n.a) << " += " << d(k) << " / (3.0 * " << v(k) << " * " << v(k) << ");\n"; break;
+        case OP_ERF: o << "    " << d(n.a) << " += " << d(k) << " * 1.1283791670955126 * exp(-" << v(n.a) << " * " << v(n.a) << ");\n"; break;
+        case OP_FABS: o << "    " << d(n.a) << " += " << d(k) << " * copysign(1.0, " << v(n.a) << ");\n"; break;
+        case OP_ATAN2:
+            o << "    { const double q = " << v(n.a) << " * " << v(n.a) << " + " << v(n.b) << " * " << v(n.b) << "; " << d(n.a) << " += " << d(k)
+              << " * " << v(n.b) << " / q; " << d(n.b) << " -= " << d(k) << " * " << v(n.a) << " / q; }\n";
+            break;
+        case OP_FMOD: o << "    " << d(n.a) << " += " << d(k) << "; " << d(n.b) << " -= " << d(k) << " * trunc(" << v(n.a) << " / " << v(n.b) << ");\n"; break;
+        case OP_FMIN: o << "    if (" << v(n.a) << " < " << v(n.b) << ") " << d(n.a) << " += " << d(k) << "; else " << d(n.b) << " += " << d(k) << ";\n"; break;
+        case OP_FMAX: o << "    if (" << v(n.a) << " > " << v(n.b) << ") " << d(n.a) << " += " << d(k) << "; else " << d(n.b) << " += " << d(k) << ";\n"; break;
+        case OP_SELECT: o << "    if (" << v(n.s) << " != 0.0) " << d(n.a) << " += " << d(k) << "; else " << d(n.b) << " += " << d(k) << ";\n"; break;
         case OP_INPUT_X: o << "    gx[" << n.a << "] = " << d(k) << ";\n"; break;
         case OP_INPUT_P: o << "    gp[" << n.a << "] += " << d(k) << ";\n"; break;
         default: break;
