@@ -73,3 +73,11 @@ def test_recorded_system_runs_through_tape_to_cuda():
     matches central finite differences (the program checks it itself)."""
     out = run("pendulum")
     assert "pendulum ok" in out, out
+
+
+def test_recorded_system_with_selects_and_elementary_functions():
+    """The wider operation surface of the tape (iIf selects on active values, erf, cbrt, atan2, fmax) through
+    tape -> CUDA -> NVRTC on the device; both sides of the select are visited along the trajectory and the adjoint matches
+    central finite differences with respect to the parameters and the initial state (the program checks it itself)."""
+    out = run("switched")
+    assert "switched ok" in out, out
