@@ -69,7 +69,7 @@ int main() {
 def test_example_clients_build():
     _ensure_lib()
     subprocess.check_call(["make", "-s", "-C", os.path.join(PKG, "examples")])
-    for name in ("harmonic", "vanderpol", "lotka"):
+    for name in ("harmonic", "vanderpol", "lotka", "pendulum", "switched", "batch_lotka"):
         assert os.path.exists(os.path.join(PKG, "examples", "build", name))
     if os.path.isdir("/root/reference/examples"):
         for name in ("ref_harmonic", "ref_vanderpol", "ref_lotka"):  # unmodified reference sources against these headers

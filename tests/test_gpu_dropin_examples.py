@@ -81,3 +81,10 @@ def test_recorded_system_with_selects_and_elementary_functions():
     central finite differences with respect to the parameters and the initial state (the program checks it itself)."""
     out = run("switched")
     assert "switched ok" in out, out
+
+
+def test_batched_cpp_api_matches_single_trajectory_driver():
+    """vectorizedadjoint_b200/include/BatchDriver.hpp: B parameter sets per call from C++ (same functor, same stepper objects as the
+    reference API), full sensitivity matrices (Nout = N); checked inside the program against single-trajectory Driver runs."""
+    out = run("batch_lotka")
+    assert "batch_lotka ok" in out, out
