@@ -116,7 +116,7 @@ def cpu_baseline(sample=0):
         import numpy as np
         import oracle
         if oracle.reference_available():
-            s4 = max(cores, (sample // 4) - (sample // 4) % cores)
+            s4 = max(cores, (sample // 8) - (sample // 8) % cores)  # ~1/4 of the main sample's time
             p = oracle.synth_params(oracle.SYS_GLV, N_SPECIES, SEED, 0, s4)
             x0 = oracle.synth_x0(oracle.SYS_GLV, N_SPECIES, p)
             seeds = np.tile(np.eye(4, N_SPECIES), (s4, 1, 1))
