@@ -63,6 +63,10 @@ def parse():
     ap.add_argument("--species", type=int, default=0, help="with --workload glv256: any other species count (same tolerances; not a BASELINE config)")
     ap.add_argument("--ckpt-policy", default="auto", choices=["auto", "recompute", "store"], help="side workloads: checkpoint policy of the engine")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side block (the other BASELINE configs, N=1 only)")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the comparison with a one-GPU run of the whole batch")
+    ap.add_argument("--no-parity-sample", action="store_true")
+    ap.add_argument("--parity-sample", type=int, default=2048, help="parameter sets compared with the CPU oracle for flip_rate (N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="parameter sets per reference-arm step (0 = auto)")
     return ap.parse_args()
@@ -160,17 +164,6 @@ def reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def _ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per full-size launch, from the committed
-    ncu --set full capture (profiles/r01_traffic_t8.json); None when no capture has been recorded."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic_t8.json")) as f:
-            d = json.load(f)
-        return d.get("dram_bytes_per_launch"), d.get("launch_parameter_sets", 1 << 20)
-    except Exception:
-        return None, None
 
 
 def workload_config(args, extra=None):
@@ -348,6 +341,171 @@ def side_workload(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# live counters: NVML GPM (DRAM bandwidth / FP64 pipe utilisation over an interval), the bench's own regression tripwire
+# ---------------------------------------------------------------------------------------------------------------------
+
+class GpmSampler:
+    """Two GPM samples around the timed region -> average DRAM bandwidth utilisation and FP64 pipe utilisation in between
+    (hardware counters sampled by the driver, no replay, no serialisation: valid next to a timed run)."""
+    DRAM_PEAK_BPS = 3996e6 * 2 * 8192 / 8  # HBM3e: 3996 MHz double data rate, 8192-bit bus = 8.18 TB/s, what DRAM_BW_UTIL is relative to
+
+    def __init__(self, index):
+        self.ok = False
+        try:
+            import pynvml as nv
+            self.nv = nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            if not nv.nvmlGpmQueryDeviceSupport(self.h).isSupportedDevice:
+                return
+            self.s0, self.s1 = nv.nvmlGpmSampleAlloc(), nv.nvmlGpmSampleAlloc()
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def start(self):
+        if self.ok:
+            try:
+                self.nv.nvmlGpmSampleGet(self.h, self.s0)
+            except Exception:
+                self.ok = False
+
+    def stop(self):
+        if not self.ok:
+            return None
+        nv = self.nv
+        try:
+            nv.nvmlGpmSampleGet(self.h, self.s1)
+            mg = nv.c_nvmlGpmMetricsGet_t()
+            mg.version = nv.NVML_GPM_METRICS_GET_VERSION
+            ids = [nv.NVML_GPM_METRIC_DRAM_BW_UTIL, nv.NVML_GPM_METRIC_FP64_UTIL, nv.NVML_GPM_METRIC_SM_UTIL]
+            mg.numMetrics = len(ids)
+            mg.sample1, mg.sample2 = self.s0, self.s1
+            for k, i in enumerate(ids):
+                mg.metrics[k].metricId = i
+            nv.nvmlGpmMetricsGet(mg)
+            vals = [mg.metrics[k].value if mg.metrics[k].nvmlReturn == 0 else None for k in range(len(ids))]
+            return {"dram_bw_util_pct": vals[0], "fp64_util_pct": vals[1], "sm_util_pct": vals[2]}
+        except Exception as ex:
+            return {"error": repr(ex)[:120]}
+
+
+def _committed_traffic():
+    """DRAM bytes per full-size launch from the newest committed ncu --set full capture (fallback when GPM is unavailable)."""
+    best = (None, None, None)
+    for name in ("r02_traffic_t8.json", "r01_traffic_t8.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            return d.get("dram_bytes_per_launch"), d.get("launch_parameter_sets", 1 << 20), name
+        except Exception:
+            continue
+    return best
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm, headline workload
+# ---------------------------------------------------------------------------------------------------------------------
+
+class DeviceShard:
+    """One GPU's part of the batch, resident in its HBM."""
+
+    def __init__(self, torch, va, device, b0, count, red):
+        self.device, self.b0, self.B = device, b0, count
+        dev = torch.device("cuda", device)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.params = torch.empty(count, NPAR, **f64)
+        self.x0 = torch.empty(count, N_SPECIES, **f64)
+        with torch.cuda.device(dev):
+            va.synth_batch_device(va.SYS_GLV, N_SPECIES, SEED, b0, count, self.params, self.x0)
+            torch.cuda.synchronize()
+        self.x_final = torch.empty(count, N_SPECIES, **f64)
+        self.lam = torch.empty(count, 1, N_SPECIES, **f64)
+        self.mu = torch.empty((1, NPAR) if red == va.REDUCE_SUM else (count, 1, NPAR), **f64)
+        self.n_acc, self.n_rej, self.status = (torch.empty(count, dtype=torch.int32, device=dev) for _ in range(3))
+        self.stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: kernels, events and NCCL ordering live on it
+
+    def args(self, va, red):
+        return dict(B=self.B, x0=self.x0, params=self.params, ti=TI, tf=TF, dt0=DT0, x_final=self.x_final, lam=self.lam, mu=self.mu,
+                    objective=va.OBJ_SUM, reduce=red, n_accept=self.n_acc, n_reject=self.n_rej, status=self.status,
+                    stream=self.stream.cuda_stream)
+
+
+def parity_sample(va, device, sample=2048):
+    """Accept/reject flips and deviations against the CPU oracle on the first `sample` seeded parameter sets (checker leg, not
+    timed): north_star allows 'documented rounding-induced flips'; this reports how many there are and how far a flipped
+    trajectory ends up from the oracle's."""
+    import numpy as np
+    import oracle
+    p = oracle.synth_params(oracle.SYS_GLV, N_SPECIES, SEED, 0, sample)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N_SPECIES, p)
+    with va.Engine(va.SYS_GLV, N_SPECIES, va.RK_CK54, True, TOL, TOL, device=device) as e:
+        g = e.forward_adjoint(x0, p, TI, TF, DT0, objective=va.OBJ_SUM)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N_SPECIES, oracle.RK_CK54, True, TOL, TOL, x0, p, TI, TF, DT0, objective=oracle.OBJ_SUM,
+                               threads=os.cpu_count() or 1)
+    flipped = (g["n_accept"] != o["n_accept"]) | (g["n_reject"] != o["n_reject"])
+
+    def rel(a, b, m):
+        if not m.any():
+            return 0.0
+        a, b = a[m].reshape(int(m.sum()), -1), b[m].reshape(int(m.sum()), -1)
+        return float((np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)).max())
+    out = {"sets": sample, "flips": int(flipped.sum()), "flip_rate": float(flipped.mean()), "oracle": "oracle/va_oracle.c (C port, pinned to reference fixtures)"}
+    for k, gk, ok in (("x_final", g["x_final"], o["x_final"]), ("dJ_dx0", g["lam"][:, 0], o["lam"][:, 0]), ("dJ_dalpha", g["mu"][:, 0], o["mu"][:, 0])):
+        out[f"max_rel_err_{k}"] = rel(gk, ok, ~flipped)
+        out[f"max_rel_err_{k}_flipped"] = rel(gk, ok, flipped)
+    return out
+
+
+def side_block(va, torch, device):
+    """The other BASELINE configs on this GPU, a few hundred ms each (device-resident, same timing rules): value + roofline fraction."""
+    out = {}
+    for name, batch, steps in (("vdp", 1 << 20, 5), ("glv16", 1 << 20, 5), ("glv256", 8192, 3), ("glv256long", 1024, 2)):
+        try:
+            out[name] = side_measure(va, torch, device, name, batch, steps)
+        except Exception as ex:
+            out[name] = {"value": None, "error": repr(ex)[:200]}
+    return out
+
+
+def side_measure(va, torch, device, name, Btot, steps, warmup=2):
+    system, n, stepper, adaptive, tol, ti, tf, dt0, max_steps, objective, stages, desc = WORKLOADS[name]
+    dev = torch.device("cuda", device)
+    npar = va.npar_of(system, n)
+    f64 = dict(dtype=torch.float64, device=dev)
+    params, x0 = torch.empty(Btot, npar, **f64), torch.empty(Btot, n, **f64)
+    va.synth_batch_device(system, n, SEED, 0, Btot, params, x0)
+    x_final, lam, mu = torch.empty(Btot, n, **f64), torch.empty(Btot, 1, n, **f64), torch.empty(1, npar, **f64)
+    n_acc, n_rej, status = (torch.empty(Btot, dtype=torch.int32, device=dev) for _ in range(3))
+    st = torch.cuda.current_stream(dev)
+    with va.Engine(system, n, stepper, adaptive, tol, tol, device=device, max_steps=max_steps) as eng:
+        def step():
+            eng.call("va_forward_adjoint_batch", Btot, x0, params, ti, tf, dt0, x_final, lam, mu, objective, va.REDUCE_SUM, n_acc, n_rej, status,
+                     stream=st.cuda_stream)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            step()
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        kernel = eng.info()["kernel_name"]
+    T, R = int(n_acc.sum(dtype=torch.int64)), int(n_rej.sum(dtype=torch.int64))
+    res = {"value": Btot / (ms * 1e-3), "unit": "gradients/s", "batch": Btot, "ms_per_step": ms, "steps": steps, "kernel": kernel,
+           "mean_accepted_steps": T / Btot, "failed_trajectories": int((status != 0).sum())}
+    if system == va.SYS_GLV:
+        flops = (stages * T + (stages - 1) * R) * (2 * n * n + 2 * n) + stages * T * (4 * n * n + 3 * n)
+        res.update(bound="fp64", achieved_tflops=flops / (ms * 1e-3) / 1e12)
+    else:
+        byts = 2 * 8 * (n + 1) * (T + Btot) + Btot * 8 * (npar + 3 * n + npar)
+        res.update(bound="hbm", achieved_gbs=byts / (ms * 1e-3) / 1e9)
+    return res
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -364,69 +522,93 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    # Two ways to use N GPUs, both through the C-ABI (include/va_engine.h "Several GPUs"):
+    #   torchrun, one rank per GPU  -> single-device engine + va_engine_comm_init; the all-reduce happens inside the call
+    #   one process, --gpus N       -> multi-device engine (va_engine_desc.devices), caller-sharded device-resident call
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+        assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+        mode, devices, total = "ranks", [local], world
+    elif args.gpus > 1:
+        assert torch.cuda.device_count() >= args.gpus, f"--gpus {args.gpus} but {torch.cuda.device_count()} visible"
+        mode, devices, total = "devices", list(range(args.gpus)), args.gpus
+    else:
+        mode, devices, total = "single", [local], 1
+    torch.cuda.set_device(devices[0])
+    dev0 = torch.device("cuda", devices[0])
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev0)  # plumbing: barrier, max-over-ranks of the timings, id broadcast
 
     N, B = N_SPECIES, args.batch
-    b0, Bl = va.shard_range(B, rank, world)
     red = va.REDUCE_SUM if args.reduce == "sum" else va.REDUCE_NONE
-    f64 = dict(dtype=torch.float64, device=dev)
-
-    params = torch.empty(Bl, NPAR, **f64)
-    x0 = torch.empty(Bl, N, **f64)
-    va.synth_batch_device(va.SYS_GLV, N, SEED, b0, Bl, params, x0)
-    x_final = torch.empty(Bl, N, **f64)
-    lam = torch.empty(Bl, 1, N, **f64)
-    mu = torch.empty((1, NPAR) if red == va.REDUCE_SUM else (Bl, 1, NPAR), **f64)
-    n_acc = torch.empty(Bl, dtype=torch.int32, device=dev)
-    n_rej = torch.empty(Bl, dtype=torch.int32, device=dev)
-    status = torch.empty(Bl, dtype=torch.int32, device=dev)
-    eng = va.Engine(va.SYS_GLV, N, va.RK_CK54, True, TOL, TOL, device=local)
+    shards = []
+    for k, d in enumerate(devices):
+        b0, cnt = va.shard_range(B, rank if mode == "ranks" else k, total)
+        shards.append(DeviceShard(torch, va, d, b0, cnt, red))
+    if mode == "devices":
+        eng = va.Engine(va.SYS_GLV, N, va.RK_CK54, True, TOL, TOL, devices=devices)
+    else:
+        eng = va.Engine(va.SYS_GLV, N, va.RK_CK54, True, TOL, TOL, device=devices[0])
+        if mode == "ranks":
+            idt = torch.zeros(va.COMM_ID_BYTES, dtype=torch.uint8, device=dev0)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(va.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
     info = eng.info()
-    side = torch.cuda.Stream(device=dev)  # a real (non-default) stream: kernels, events and NCCL ordering all live on it
-    torch.cuda.set_stream(side)
-    stream = side.cuda_stream
+    sh_args = [s.args(va, red) for s in shards]
 
     def step():
-        eng.call("va_forward_adjoint_batch", Bl, x0, params, TI, TF, DT0, x_final, lam, mu, va.OBJ_SUM, red, n_acc, n_rej, status,
-                 stream=stream)
-        if world > 1 and red == va.REDUCE_SUM:
-            dist.all_reduce(mu)  # 33 KB, the only collective on the path
+        # ONE C-ABI call per step; with several GPUs the summed gradient is all-reduced inside it (ncclAllReduce, 33 KB)
+        if mode == "devices":
+            eng.call_sharded(sh_args)
+        else:
+            a = dict(sh_args[0])
+            Bn = a.pop("B")
+            eng.call("va_forward_adjoint_batch", Bn, a.pop("x0"), a.pop("params"), a.pop("ti"), a.pop("tf"), a.pop("dt0"), a.pop("x_final"),
+                     a.pop("lam"), a.pop("mu"), **a)
 
     def barrier():
+        for s in shards:
+            torch.cuda.synchronize(s.device)
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 1)):
         step()
     barrier()
-    launches0 = eng.info()["kernel_launches"]
-    clocks = ClockSampler(local) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0, coll0 = eng.info()["kernel_launches"], eng.info()["collectives"]
+    clocks = ClockSampler(devices[0]) if rank == 0 else None
+    gpm = GpmSampler(devices[0]) if rank == 0 else None
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] for _ in shards]
     barrier()
-    ev[0].record()
+    if gpm:
+        gpm.start()
+    for s, e in zip(shards, ev):
+        e[0].record(s.stream)
     for k in range(args.steps):
         step()
-        ev[k + 1].record()
+        for s, e in zip(shards, ev):
+            e[k + 1].record(s.stream)
     barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    gpm_vals = gpm.stop() if gpm else None
+    total_ms = max(e[0].elapsed_time(e[-1]) for e in ev)  # slowest GPU of this process
+    step_ms = [ev[0][k].elapsed_time(ev[0][k + 1]) for k in range(args.steps)]
     clk = clocks.stop() if clocks else None
     launches = eng.info()["kernel_launches"] - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    collectives = eng.info()["collectives"] - coll0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev0)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = B * args.steps / (total_ms * 1e-3)
 
-    # work actually done (for the roofline): accepted / rejected steps of this rank's shard
-    T_sum = int(n_acc.sum(dtype=torch.int64).item())
-    R_sum = int(n_rej.sum(dtype=torch.int64).item())
-    bad = int((status != 0).sum().item())
+    # work actually done (for the roofline): accepted / rejected steps of the first shard of this process
+    s0 = shards[0]
+    Bl = s0.B
+    T_sum = int(s0.n_acc.sum(dtype=torch.int64).item())
+    R_sum = int(s0.n_rej.sum(dtype=torch.int64).item())
+    bad = int((s0.status != 0).sum().item())
     f_rhs, f_vjp = 2 * N * N + 2 * N, 4 * N * N + 3 * N
     # executed: store-stages policy, no stage recompute in the reverse sweep; K0 is not re-evaluated after a rejection
     flops_exec = (STAGES * T_sum + (STAGES - 1) * R_sum) * f_rhs + STAGES * T_sum * f_vjp
@@ -435,12 +617,17 @@ def main():
     kernel_ms = sorted(step_ms)[len(step_ms) // 2]
 
     line = {
-        "metric": METRIC, "value": value, "unit": "gradients/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": "gradients/s", "n_gpus": total, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args), "gpu_launches": launches,
+        "data": "synthetic", "config": workload_config(args), "gpu_launches": launches * (world if mode == "ranks" else 1),
     }
+    line["config"]["multi_gpu"] = {"single": "one GPU", "ranks": f"{world} processes, one single-device engine each, attached with va_engine_comm_init",
+                                   "devices": f"one process, one multi-device engine over {total} GPUs (va_engine_desc.devices)"}[mode]
+    if total > 1:
+        line["collective"] = {"where": "inside va_forward_adjoint_batch (libva_engine.so: ncclAllReduce, ncclDouble, ncclSum, 33 KB)",
+                              "calls_in_timed_region_per_gpu": collectives // max(len(shards), 1), "nccl_version": eng.info()["nccl_version"]}
     if rank == 0:
-        peak_tf = va.measure_fp64_peak(local)
+        peak_tf = va.measure_fp64_peak(devices[0])
         hbm_meas = None
         try:
             hbm_meas = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -448,9 +635,18 @@ def main():
             pass
         ach = flops_exec / (kernel_ms * 1e-3) / 1e12
         alg_bytes = Bl * (8 * NPAR + 8 * N * 3) + (0 if red == va.REDUCE_SUM else Bl * 8 * NPAR)
+        traffic, traffic_source = None, None
+        if gpm_vals and gpm_vals.get("dram_bw_util_pct") is not None:
+            traffic = int(gpm_vals["dram_bw_util_pct"] / 100.0 * GpmSampler.DRAM_PEAK_BPS * kernel_ms * 1e-3)
+            traffic_source = ("live: NVML GPM DRAM_BW_UTIL averaged over the timed region x 8.18 TB/s (3996 MHz x 2 x 8192 bit) x the launch "
+                              "duration; cross-checked against the ncu --set full capture in profiles/")
+        else:
+            tb = _committed_traffic()
+            if tb[0]:
+                traffic, traffic_source = int(tb[0] * Bl / tb[1]), f"committed ncu --set full capture profiles/{tb[2]} scaled to this shard (GPM unavailable)"
         line["roofline"] = {
             "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-            "traffic": (lambda tb: int(tb[0] * Bl / tb[1]) if tb[0] else None)(_ncu_traffic()),
+            "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": alg_bytes, "gpm": gpm_vals,
             "peak_source": "DFMA microbenchmark run live on this GPU (va_measure_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
             "kernel": "k_glv_t8<TabCK54,adaptive,exact> (va_glv_t8.cu; one launch per step per GPU, %d CTAs x %d threads, 64 threads per "
                       "trajectory; + one row-reduction kernel over the per-slot partial sums)" % (info["sm_count"] * info["ctas_per_sm"], info["threads_per_cta"]),
@@ -464,60 +660,134 @@ def main():
         }
         line["clocks"] = clk
 
+    # ---- N > 1: is the sharded result the one-GPU result? (outside the timed region) ----------------------------------
+    if total > 1 and red == va.REDUCE_SUM and not args.no_check:
+        try:
+            acc_tot = torch.stack([s.n_acc.sum(dtype=torch.int64).to(dev0) for s in shards]).sum()
+            xf_tot = torch.stack([s.x_final.sum().to(dev0) for s in shards]).sum()
+            if world > 1:
+                dist.all_reduce(acc_tot)
+                dist.all_reduce(xf_tot)
+            if rank == 0:
+                chk = DeviceShard(torch, va, devices[0], 0, B, red)  # the whole batch on ONE GPU, its own engine, no communicator
+                with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, TOL, TOL, device=devices[0]) as e1:
+                    a = chk.args(va, red)
+                    Bn = a.pop("B")
+                    e1.call("va_forward_adjoint_batch", Bn, a.pop("x0"), a.pop("params"), a.pop("ti"), a.pop("tf"), a.pop("dt0"), a.pop("x_final"),
+                            a.pop("lam"), a.pop("mu"), **a)
+                    torch.cuda.synchronize(devices[0])
+                scale = float(chk.mu.abs().max())
+                line["multi_gpu_check"] = {
+                    "what": f"all-reduced summed gradient of the {total}-GPU run vs the same 2^20 parameter sets on one GPU (separate engine, no communicator)",
+                    "mu_max_rel_diff": float((s0.mu - chk.mu).abs().max()) / scale,
+                    "first_shard_x_final_bit_identical": bool(torch.equal(s0.x_final, chk.x_final[s0.b0:s0.b0 + s0.B])),
+                    "first_shard_dJ_dx0_bit_identical": bool(torch.equal(s0.lam, chk.lam[s0.b0:s0.b0 + s0.B])),
+                    "accepted_steps_total_equal": int(acc_tot.item()) == int(chk.n_acc.sum(dtype=torch.int64).item()),
+                    "x_final_checksum_rel_diff": abs(float(xf_tot.item()) - float(chk.x_final.sum().item())) / abs(float(chk.x_final.sum().item())),
+                }
+                del chk
+                torch.cuda.empty_cache()
+        except Exception as ex:
+            line["multi_gpu_check"] = {"error": repr(ex)[:300]}
+
     # ---- end to end: host buffers through the C-ABI, copies inside the timed region ------------------------------------
     if not args.no_e2e:
         try:
-            hp = torch.empty(Bl, NPAR, dtype=torch.float64, pin_memory=True)
-            hx0 = torch.empty(Bl, N, dtype=torch.float64, pin_memory=True)
-            hp.copy_(params)
-            hx0.copy_(x0)
-            hxf = torch.empty(Bl, N, dtype=torch.float64, pin_memory=True)
-            hlam = torch.empty(Bl, 1, N, dtype=torch.float64, pin_memory=True)
-            hmu = torch.empty((1, NPAR) if red == va.REDUCE_SUM else (Bl, 1, NPAR), dtype=torch.float64, pin_memory=True)
-            e2e_steps = max(1, min(args.steps, 3))
-
-            def e2e_step():
-                eng.call("va_forward_adjoint_batch", Bl, hx0.numpy(), hp.numpy(), TI, TF, DT0, hxf.numpy(), hlam.numpy(), hmu.numpy(),
-                         va.OBJ_SUM, red)
-                if world > 1 and red == va.REDUCE_SUM:
-                    m = hmu.to(dev, non_blocking=True)
-                    dist.all_reduce(m)
-                    hmu.copy_(m)
-
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
-            barrier()
-            dt = time.perf_counter() - t0
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-            h2d = Bl * 8 * (NPAR + N)
-            d2h = Bl * 8 * 2 * N + hmu.numel() * 8
-            line["e2e"] = {"value": B * e2e_steps / dt, "unit": "gradients/s", "h2d_bytes_per_step": h2d * world,
-                           "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
-                           "note": "va_forward_adjoint_batch with pinned HOST buffers; chunked 3-stream pipeline inside the call"}
-            if rank == 0:
-                same = bool(torch.equal(hxf.to(dev), x_final))
-                line["e2e"]["matches_device_resident_run"] = same
-            del hp, hx0, hxf, hlam, hmu
+            line["e2e"] = e2e_leg(args, torch, dist, va, eng, shards, mode, world, rank, total, red, barrier)
         except Exception as ex:  # pinned memory not available etc.: report, do not hide
             line["e2e"] = {"value": None, "unit": "gradients/s", "error": repr(ex)[:300]}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            cb, _, _ = cpu_baseline(args.cpu_sample)
-            line["cpu_baseline"] = cb
-        except Exception as ex:
-            line["cpu_baseline"] = {"value": None, "error": repr(ex)[:300]}
     eng.close()
+    del shards, sh_args, s0
+    torch.cuda.empty_cache()
+
+    if rank == 0 and total == 1:
+        if not args.no_parity_sample:
+            try:
+                line["parity_sample"] = parity_sample(va, devices[0], args.parity_sample)
+                line["flip_rate"] = line["parity_sample"]["flip_rate"]
+            except Exception as ex:
+                line["parity_sample"] = {"error": repr(ex)[:300]}
+        if not args.no_side:
+            line["side"] = side_block(va, torch, devices[0])
+            pk = line.get("roofline", {}).get("peak")
+            hb = line.get("roofline", {}).get("hbm", {}).get("peak_gbs")
+            for v in line["side"].values():
+                if v.get("bound") == "fp64" and pk:
+                    v["frac"] = v["achieved_tflops"] / pk
+                elif v.get("bound") == "hbm" and hb:
+                    v["frac"] = v["achieved_gbs"] / hb
+        if not args.no_cpu_baseline:
+            try:
+                cb, _, _ = cpu_baseline(args.cpu_sample)
+                line["cpu_baseline"] = cb
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "error": repr(ex)[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_leg(args, torch, dist, va, eng, shards, mode, world, rank, total, red, barrier):
+    """The same pass through the reference-facing C-ABI call with HOST buffers (page-locked, from va_host_alloc): host->device
+    copies of the parameters and device->host copies of the results are inside the timed region, every step."""
+    import numpy as np
+    N = N_SPECIES
+    Bl = sum(s.B for s in shards)  # this process's parameter sets (all of them in one-process modes)
+    flags = int(os.environ.get("VA_BENCH_HOST_FLAGS", str(va.HOST_NUMA_LOCAL)))
+    dev0 = shards[0].device
+    hp = va.host_alloc((Bl, NPAR), flags=flags, device=dev0)
+    hx0 = va.host_alloc((Bl, N), flags=flags, device=dev0)
+    off = 0
+    for s in shards:  # fill the host inputs from the device-resident ones (not timed)
+        torch.from_numpy(hp.array[off:off + s.B]).copy_(s.params)
+        torch.from_numpy(hx0.array[off:off + s.B]).copy_(s.x0)
+        off += s.B
+    hxf = va.host_alloc((Bl, N), device=dev0)
+    hlam = va.host_alloc((Bl, 1, N), device=dev0)
+    hmu = va.host_alloc((1, NPAR) if red == va.REDUCE_SUM else (Bl, 1, NPAR), device=dev0)
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():  # one C-ABI call; a multi-device engine splits the host batch itself, ranks all-reduce inside the call
+        eng.call("va_forward_adjoint_batch", Bl, hx0.array, hp.array, TI, TF, DT0, hxf.array, hlam.array, hmu.array, va.OBJ_SUM, red)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = time.perf_counter() - t0
+    dev = torch.device("cuda", dev0)
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    ranks = world if mode == "ranks" else 1
+    h2d = Bl * 8 * (NPAR + N) * ranks
+    d2h = (Bl * 8 * 2 * N + hmu.array.size * 8) * ranks
+    out = {"value": args.batch * e2e_steps / dt, "unit": "gradients/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "note": "va_forward_adjoint_batch with page-locked HOST buffers (va_host_alloc); chunked 3-stream pipeline per GPU inside the call"}
+    if rank == 0:
+        out["matches_device_resident_run"] = bool(np.array_equal(hxf.array[:shards[0].B], shards[0].x_final.cpu().numpy()))
+    # the ceiling: what the box delivers host->device with all GPUs of the run copying concurrently, from THESE buffers' kind
+    try:
+        barrier()
+        per, agg = va.measure_h2d_copy([s.device for s in shards], nbytes=1 << 30, reps=3, flags=flags)
+        a = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(a)
+        peak = float(a.item())
+        ach = h2d / (dt / e2e_steps) / 1e9
+        out["roofline"] = {"bound": "h2d", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "peak_source": f"va_measure_h2d_copy: 1 GiB per GPU from page-locked host memory, all {total} GPU(s) of this run copying "
+                                          "concurrently, best of 3, summed over GPUs (measured in this run)",
+                           "per_gpu_gbs_this_process": per}
+    except Exception as ex:
+        out["roofline"] = {"error": repr(ex)[:200]}
+    for h in (hp, hx0, hxf, hlam, hmu):
+        h.free()
+    return out
 
 
 if __name__ == "__main__":

@@ -24,6 +24,20 @@
  *   va_forward_adjoint_batch the two calls above fused (the benchmarked call; checkpoints never leave the GPU)
  *   va_get_checkpoints       Driver::GetT / GetTime / GetDt / GetState          lib/include/Driver.hpp:53-66
  *   va_engine_destroy        delete_driver_handle(void*)                        lib/include/Driver.hpp:81-85
+ *   va_forward_adjoint_batch_sharded, va_comm_unique_id, va_engine_comm_init
+ *                            nothing: the reference is single-threaded and single-device; its own note that the AAD
+ *                            workspace "needs to spawn several workspaces to allow multi-threading" is the closest it
+ *                            gets                                               lib/include/AadData.hpp:32
+ *
+ * Several GPUs. Parameter sets are independent, so a batch shards contiguously (set b of B goes to device
+ * g = the shard whose range [b0_g, b0_g + count_g) holds b; counts differ by at most one) and nothing is exchanged during
+ * integration. Two ways to use G GPUs, both below this C line:
+ *   (1) one process, one engine: va_engine_desc.n_devices = G, .devices = ordinals. Every batch call shards over the
+ *       listed GPUs (one host worker thread and one set of streams per GPU). With VA_REDUCE_SUM the per-GPU sums are
+ *       combined by ONE ncclAllReduce(ncclDouble, ncclSum) inside the call (communicator from ncclCommInitAll).
+ *   (2) one process per GPU (torchrun / MPI): every rank creates a single-device engine and attaches it to a communicator
+ *       with va_comm_unique_id (rank 0, then broadcast by the launcher's own means) + va_engine_comm_init (all ranks).
+ *       From then on a VA_REDUCE_SUM call on that engine is collective: it ends in the same ncclAllReduce over the ranks.
  *
  * The reference has no batch axis (one Driver = one trajectory; its SIMD lanes carry adjoint seeds). Here the batch of
  * parameter sets is the parallel axis; B = 1 reproduces the reference call for call.
@@ -45,7 +59,7 @@
 extern "C" {
 #endif
 
-#define VA_API_VERSION 1
+#define VA_API_VERSION 2
 
 typedef struct va_engine va_engine;
 
@@ -78,12 +92,13 @@ typedef struct va_engine_desc {
     int32_t stepper;     /* va_stepper                                                                         */
     int32_t adaptive;    /* 0: fixed step (stepper_tag loop), 1: controlled (make_controlled<stepper>(abs,rel)) */
     double eps_abs, eps_rel;
-    int32_t device;      /* CUDA ordinal                                                                       */
+    int32_t device;      /* CUDA ordinal (ignored when n_devices > 0)                                          */
     int32_t max_steps;   /* checkpoint capacity per trajectory (accepted steps); 0 = default                   */
     int32_t ckpt_policy; /* va_ckpt_policy                                                                     */
-    int32_t reserved0;
+    int32_t n_devices;   /* 0: one GPU, `device`; G >= 1: every batch is sharded over devices[0..G)            */
     double workspace_fraction; /* share of free HBM the checkpoint arena may take (0 = default 0.5)            */
     const char *tape_cuda_src; /* VA_SYS_TAPE: CUDA source of the rhs/vjp device functors (see va_tape.h)      */
+    const int32_t *devices;    /* [n_devices] distinct CUDA ordinals (read during va_engine_create only)       */
 } va_engine_desc;
 
 typedef struct va_batch_args {
@@ -113,6 +128,11 @@ typedef struct va_engine_info {
     char device_name[64];
     char kernel_name[32];    /* the kernel that serves this engine: k_scalar, k_glv_wide, k_glv_t8, k_glv_stream, k_glv_ring,
                                 k_glv_pair, or jit (run-time compiled thread-per-trajectory kernels of a recorded system)  */
+    int32_t n_devices;       /* GPUs this engine shards over (1 for a single-device engine)                      */
+    int32_t comm_world;      /* ranks of the attached communicator (n_devices, or va_engine_comm_init's world; 0 = none) */
+    int32_t comm_rank;       /* this engine's rank in it (multi-device engine: 0)                                */
+    int32_t nccl_version;    /* ncclGetVersion() of the library in use, 0 when no communicator is attached       */
+    int64_t collectives;     /* ncclAllReduce calls issued since creation (all devices of the engine)            */
 } va_engine_info;
 
 #ifndef __CUDACC_RTC__ /* the enums and structs above are also seen by run-time compiled device code */
@@ -124,6 +144,22 @@ const char *va_last_error(void);
 int va_forward_batch(va_engine *e, const va_batch_args *args);
 int va_adjoint_batch(va_engine *e, const va_batch_args *args);
 int va_forward_adjoint_batch(va_engine *e, const va_batch_args *args);
+
+/* Multi-device engine (n_devices = G), caller-sharded form: shards[g] describes the part of the batch that lives on
+ * devices[g] (its own batch count and buffers; VA_MEM_DEVICE buffers must be on that GPU, shards[g].stream a stream of that
+ * GPU or NULL). All G shards run concurrently; ti/tf/dt0/objective/reduce/mem must agree. With VA_REDUCE_SUM every
+ * shards[g].mu receives the sum over ALL shards (one ncclAllReduce). va_forward_adjoint_batch on a multi-device engine
+ * is this call with the contiguous split of a VA_MEM_HOST batch (mu then is one host buffer). */
+int va_forward_adjoint_batch_sharded(va_engine *e, int32_t n_shards, const va_batch_args *shards);
+/* shard g of `world`: first parameter set and count of the contiguous split used by the multi-device calls */
+void va_shard_range(int64_t batch, int32_t g, int32_t world, int64_t *b0, int64_t *count);
+
+/* One process per GPU. va_comm_unique_id: rank 0 obtains an opaque id (VA_COMM_ID_BYTES) and hands it to the other ranks
+ * by the launcher's means; va_engine_comm_init: collective over all `world` ranks, attaches a single-device engine to the
+ * communicator. Afterwards VA_REDUCE_SUM calls on the engine are collective and return the sum over all ranks. */
+#define VA_COMM_ID_BYTES 128
+int va_comm_unique_id(void *id, int32_t id_bytes);
+int va_engine_comm_init(va_engine *e, const void *id, int32_t id_bytes, int32_t rank, int32_t world);
 
 /* Checkpoints of trajectory b of the last va_forward_batch call: count = T+1 entries (t_n, x_n[n_state]).
  * Pass t = x = NULL to query the count only. */
@@ -142,6 +178,20 @@ int va_synth_batch_device(int32_t system, int32_t n_state, uint64_t seed, int64_
 /* Microbenchmarks for the roofline denominators, measured on the device the call runs on. */
 int va_measure_fp64_peak(int32_t device, double *tflops);
 int va_measure_hbm_copy(int32_t device, double *gbytes_per_s);
+/* Host -> device copy ceiling (the denominator of the end-to-end number): `bytes` per device from page-locked host memory to
+ * each of devices[0..n), all devices copying CONCURRENTLY, best of `reps`; gbytes_per_s[g] = rate of device g, the aggregate
+ * is their sum over the common wall time, returned in *aggregate. `host` may be NULL (the call allocates its own buffers with
+ * va_host_alloc(flags)) or a caller buffer of n * bytes (e.g. the bench's own input buffer: measures THAT memory). */
+int va_measure_h2d_copy(const int32_t *devices, int32_t n, int64_t bytes, int32_t reps, int32_t flags, const void *host,
+                        double *gbytes_per_s, double *aggregate);
+
+/* Page-locked host buffers for VA_MEM_HOST calls. flags: VA_HOST_WRITE_COMBINED for input-only buffers (parameters, x0:
+ * the CPU only writes them; uncached, so the GPU's reads need no cache snoops), VA_HOST_NUMA_LOCAL binds the pages to the
+ * NUMA node of `device` when the host exposes more than one node. Plain malloc'ed memory also works in every call (the
+ * copies then go through the driver's staging and are slower). */
+enum va_host_flags { VA_HOST_DEFAULT = 0, VA_HOST_WRITE_COMBINED = 1, VA_HOST_NUMA_LOCAL = 2 };
+int va_host_alloc(void **ptr, int64_t bytes, int32_t flags, int32_t device);
+int va_host_free(void *ptr);
 #endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus

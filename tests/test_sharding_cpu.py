@@ -52,6 +52,29 @@ def test_shard_ranges_partition_the_batch():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
 
 
+def test_c_abi_shard_range_is_the_same_split():
+    """va_shard_range (what a multi-device engine uses inside the call) == shard_range (what one-process-per-GPU launchers use)."""
+    import ctypes
+    L = va.lib()
+    for batch in (0, 1, 7, 13, 1 << 20, (1 << 20) + 5):
+        for world in (1, 2, 3, 4, 8):
+            for g in range(world):
+                b0, cnt = ctypes.c_int64(), ctypes.c_int64()
+                L.va_shard_range(batch, g, world, ctypes.byref(b0), ctypes.byref(cnt))
+                assert (b0.value, cnt.value) == va.shard_range(batch, g, world)
+
+
+def test_multi_device_engine_needs_a_gpu_and_validates_its_device_list():
+    """No GPU here: creation must fail loudly (no CPU path), and a malformed device list is rejected before anything else."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(va.EngineError):
+        va.Engine(va.SYS_GLV, 8, va.RK_CK54, True, 1e-8, 1e-8, devices=[0, 1])
+    with pytest.raises(va.EngineError, match="distinct"):
+        va.Engine(va.SYS_GLV, 8, va.RK_CK54, True, 1e-8, 1e-8, devices=[0, 0])
+    assert len(va.comm_unique_id()) == va.COMM_ID_BYTES  # NCCL is bound at run time and present in the image
+
+
 def test_two_rank_summed_gradient_matches_unsharded():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

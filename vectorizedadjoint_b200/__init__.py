@@ -21,7 +21,7 @@ import numpy as np
 
 __all__ = ["Engine", "EngineError", "lib", "build", "SYS_HARMONIC", "SYS_VANDERPOL", "SYS_GLV", "RK_EULER", "RK_RK4", "RK_CK54",
            "RK_DOPRI5", "RK_RKF78", "OBJ_SEED", "OBJ_SUM", "OBJ_HALF_NORM2", "REDUCE_NONE", "REDUCE_SUM", "synth_batch_device",
-           "measure_fp64_peak", "measure_hbm_copy", "npar_of", "shard_range"]
+           "measure_fp64_peak", "measure_hbm_copy", "measure_h2d_copy", "host_alloc", "HostBuffer", "comm_unique_id", "npar_of", "shard_range"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VA_ENGINE_LIB") or os.path.join(HERE, "libva_engine.so")  # VA_ENGINE_LIB: experiment builds
@@ -34,8 +34,13 @@ MEM_HOST, MEM_DEVICE = 0, 1
 CKPT_AUTO, CKPT_RECOMPUTE, CKPT_STORE_STAGES = 0, 1, 2
 TRAJ_OK, TRAJ_CKPT_OVERFLOW, TRAJ_NO_PROGRESS, TRAJ_NONFINITE = 0, 1, 2, 4
 
+HOST_DEFAULT, HOST_WRITE_COMBINED, HOST_NUMA_LOCAL = 0, 1, 2
+COMM_ID_BYTES = 128
+
 EXPORTS = ["va_engine_create", "va_engine_destroy", "va_engine_get_info", "va_last_error", "va_forward_batch", "va_adjoint_batch",
-           "va_forward_adjoint_batch", "va_get_checkpoints", "va_tape_compile_check", "va_synth_batch_device", "va_measure_fp64_peak", "va_measure_hbm_copy"]
+           "va_forward_adjoint_batch", "va_forward_adjoint_batch_sharded", "va_shard_range", "va_comm_unique_id", "va_engine_comm_init",
+           "va_get_checkpoints", "va_tape_compile_check", "va_synth_batch_device", "va_measure_fp64_peak", "va_measure_hbm_copy",
+           "va_measure_h2d_copy", "va_host_alloc", "va_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -45,8 +50,8 @@ class EngineError(RuntimeError):
 class _Desc(ctypes.Structure):
     _fields_ = [("system", ctypes.c_int32), ("n_state", ctypes.c_int32), ("n_par", ctypes.c_int32), ("n_out", ctypes.c_int32),
                 ("stepper", ctypes.c_int32), ("adaptive", ctypes.c_int32), ("eps_abs", ctypes.c_double), ("eps_rel", ctypes.c_double),
-                ("device", ctypes.c_int32), ("max_steps", ctypes.c_int32), ("ckpt_policy", ctypes.c_int32), ("reserved0", ctypes.c_int32),
-                ("workspace_fraction", ctypes.c_double), ("tape_cuda_src", ctypes.c_char_p)]
+                ("device", ctypes.c_int32), ("max_steps", ctypes.c_int32), ("ckpt_policy", ctypes.c_int32), ("n_devices", ctypes.c_int32),
+                ("workspace_fraction", ctypes.c_double), ("tape_cuda_src", ctypes.c_char_p), ("devices", ctypes.POINTER(ctypes.c_int32))]
 
 
 class _Args(ctypes.Structure):
@@ -62,7 +67,8 @@ class _Info(ctypes.Structure):
                 ("ckpt_policy", ctypes.c_int32), ("max_steps", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32),
                 ("threads_per_cta", ctypes.c_int32), ("workspace_bytes", ctypes.c_int64), ("chunk_trajectories", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_int64), ("last_kernel_ms", ctypes.c_double), ("device_name", ctypes.c_char * 64),
-                ("kernel_name", ctypes.c_char * 32)]
+                ("kernel_name", ctypes.c_char * 32), ("n_devices", ctypes.c_int32), ("comm_world", ctypes.c_int32),
+                ("comm_rank", ctypes.c_int32), ("nccl_version", ctypes.c_int32), ("collectives", ctypes.c_int64)]
 
 
 def build(verbose: bool = False) -> str:
@@ -96,6 +102,15 @@ def lib():
                                          ctypes.POINTER(ctypes.c_int32)]
         L.va_synth_batch_device.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.va_forward_adjoint_batch_sharded.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_Args)]
+        L.va_shard_range.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        L.va_shard_range.restype = None
+        L.va_comm_unique_id.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+        L.va_engine_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.va_measure_h2d_copy.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.va_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]
+        L.va_host_free.argtypes = [ctypes.c_void_p]
         L.va_measure_fp64_peak.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
         L.va_measure_hbm_copy.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
         _lib = L
@@ -109,7 +124,8 @@ def _check(rc: int, what: str):
 
 def shard_range(batch: int, rank: int, world: int):
     """Contiguous shard [b0, b0 + count) of a batch of parameter sets for `rank` of `world` (the only multi-GPU
-    decomposition on this path: independent trajectories, no data-path collective)."""
+    decomposition on this path: independent trajectories, no data-path collective). Same arithmetic as the C-ABI's
+    va_shard_range (kept in Python too so that host-side logic can be tested without the library)."""
     base, rem = divmod(batch, world)
     count = base + (1 if rank < rem else 0)
     b0 = rank * base + min(rank, rem)
@@ -137,13 +153,31 @@ class Engine:
 
     def __init__(self, system: int, n_state: int, stepper: int, adaptive: bool, eps_abs: float = 0.0, eps_rel: float = 0.0,
                  n_out: int = 1, device: int = 0, max_steps: int = 0, n_par: int | None = None, workspace_fraction: float = 0.0,
-                 ckpt_policy: int = 0):
+                 ckpt_policy: int = 0, devices=None, tape_cuda_src: str | None = None):
+        """devices=[g0, g1, ...]: a multi-device engine -- every batch call shards over those GPUs inside the C-ABI."""
         self._h = ctypes.c_void_p()
         self.system, self.n, self.n_out = system, n_state, n_out
         self.npar = npar_of(system, n_state) if n_par is None else n_par
-        d = _Desc(system, n_state, self.npar, n_out, stepper, int(adaptive), eps_abs, eps_rel, device, max_steps, ckpt_policy, 0,
-                  workspace_fraction, None)
+        self.devices = list(devices) if devices else [device]
+        dev_arr = (ctypes.c_int32 * len(self.devices))(*self.devices) if devices else None
+        d = _Desc(system, n_state, self.npar, n_out, stepper, int(adaptive), eps_abs, eps_rel, self.devices[0], max_steps, ckpt_policy,
+                  len(self.devices) if devices else 0, workspace_fraction, tape_cuda_src.encode() if tape_cuda_src else None, dev_arr)
         _check(lib().va_engine_create(ctypes.byref(d), ctypes.byref(self._h)), "va_engine_create")
+
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        """One process per GPU: attach this (single-device) engine to the communicator identified by `comm_id`
+        (comm_unique_id() of rank 0, handed around by the launcher). Collective over all ranks. Afterwards REDUCE_SUM
+        calls end in one ncclAllReduce over the ranks, inside the C-ABI call."""
+        buf = ctypes.create_string_buffer(bytes(comm_id), COMM_ID_BYTES)
+        _check(lib().va_engine_comm_init(self._h, buf, COMM_ID_BYTES, rank, world), "va_engine_comm_init")
+
+    def call_sharded(self, shards):
+        """Multi-device engine, caller-sharded: `shards` = one dict per device with the keyword arguments of call()
+        (B, x0, params, ti, tf, dt0, x_final, lam, mu, objective, reduce, n_accept, n_reject, status, stream)."""
+        arr = (_Args * len(shards))()
+        for k, sh in enumerate(shards):
+            arr[k] = self._args(**sh)
+        _check(lib().va_forward_adjoint_batch_sharded(self._h, len(shards), arr), "va_forward_adjoint_batch_sharded")
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -173,6 +207,12 @@ class Engine:
     # ---- raw call: caller-provided buffers (numpy = host memory, torch.cuda = device memory) ----------------------
     def call(self, which: str, B: int, x0, params, ti, tf, dt0, x_final, lam, mu, objective=OBJ_SUM, reduce=REDUCE_NONE,
              n_accept=None, n_reject=None, status=None, stream=None):
+        a = self._args(B, x0, params, ti, tf, dt0, x_final, lam, mu, objective, reduce, n_accept, n_reject, status, stream)
+        _check(getattr(lib(), which)(self._h, ctypes.byref(a)), which)
+
+    @staticmethod
+    def _args(B, x0, params, ti, tf, dt0, x_final, lam, mu, objective=OBJ_SUM, reduce=REDUCE_NONE, n_accept=None, n_reject=None,
+              status=None, stream=None):
         bufs = [b for b in (x0, params, x_final, lam, mu, n_accept, n_reject, status) if b is not None]
         on_dev = [_is_torch(b) and b.is_cuda for b in bufs]
         if any(on_dev) and not all(on_dev):
@@ -182,10 +222,9 @@ class Engine:
                 assert b.is_contiguous()
             else:
                 assert b.flags["C_CONTIGUOUS"]
-        a = _Args(B, _ptr(x0), _ptr(params), ti, tf, dt0, objective, reduce, MEM_DEVICE if all(on_dev) and bufs else MEM_HOST, 0,
-                  _ptr(x_final), _ptr(lam), _ptr(mu), _ptr(n_accept), _ptr(n_reject), _ptr(status),
-                  ctypes.c_void_p(stream) if stream else None)
-        _check(getattr(lib(), which)(self._h, ctypes.byref(a)), which)
+        return _Args(B, _ptr(x0), _ptr(params), ti, tf, dt0, objective, reduce, MEM_DEVICE if all(on_dev) and bufs else MEM_HOST, 0,
+                     _ptr(x_final), _ptr(lam), _ptr(mu), _ptr(n_accept), _ptr(n_reject), _ptr(status),
+                     ctypes.c_void_p(stream) if stream else None)
 
     # ---- convenience (numpy in / numpy out) -------------------------------------------------------------------------
     def forward_adjoint(self, x0, params, ti, tf, dt0, objective=OBJ_SUM, seeds=None, reduce=REDUCE_NONE):
@@ -242,3 +281,55 @@ def measure_hbm_copy(device: int = 0) -> float:
     v = ctypes.c_double()
     _check(lib().va_measure_hbm_copy(device, ctypes.byref(v)), "va_measure_hbm_copy")
     return v.value
+
+
+def comm_unique_id() -> bytes:
+    """Opaque id of a new communicator (rank 0 calls this, the launcher broadcasts it, every rank passes it to
+    Engine.comm_init)."""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().va_comm_unique_id(buf, COMM_ID_BYTES), "va_comm_unique_id")
+    return buf.raw
+
+
+class HostBuffer:
+    """Page-locked host memory from va_host_alloc, viewed as a numpy array (flags: HOST_WRITE_COMBINED for input-only
+    buffers, HOST_NUMA_LOCAL to bind the pages to the GPU's NUMA node)."""
+
+    def __init__(self, shape, dtype=np.float64, flags: int = HOST_DEFAULT, device: int = 0):
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = ctypes.c_void_p()
+        _check(lib().va_host_alloc(ctypes.byref(self._p), max(self.nbytes, 1), flags, device), "va_host_alloc")
+        raw = (ctypes.c_char * max(self.nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().va_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def host_alloc(shape, dtype=np.float64, flags: int = HOST_DEFAULT, device: int = 0) -> HostBuffer:
+    return HostBuffer(shape, dtype, flags, device)
+
+
+def measure_h2d_copy(devices, nbytes: int = 1 << 30, reps: int = 3, flags: int = HOST_DEFAULT, host_ptr: int | None = None):
+    """Host->device copy ceiling with all `devices` copying concurrently: (per-device GB/s list, aggregate GB/s)."""
+    devs = (ctypes.c_int32 * len(devices))(*devices)
+    per = (ctypes.c_double * len(devices))()
+    agg = ctypes.c_double()
+    _check(lib().va_measure_h2d_copy(devs, len(devices), nbytes, reps, flags, ctypes.c_void_p(host_ptr) if host_ptr else None, per,
+                                     ctypes.byref(agg)), "va_measure_h2d_copy")
+    return list(per), agg.value

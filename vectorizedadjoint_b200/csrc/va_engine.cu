@@ -19,96 +19,22 @@
 #include <string>
 #include <vector>
 
-#include "va_common.cuh"
-#include "va_jit.h"
+#include "va_engine_impl.h"
 
 namespace {
-
 thread_local std::string g_last_error;
+} // namespace
 
-int fail(int code, const std::string &msg)
+int va_fail(int code, const std::string &msg)
 {
     g_last_error = msg;
     return code;
 }
+const std::string &va_tls_error() { return g_last_error; }
 
-#define VA_CUDA(call)                                                                                       \
-    do {                                                                                                    \
-        cudaError_t err__ = (call);                                                                         \
-        if (err__ != cudaSuccess)                                                                           \
-            return fail(err__ == cudaErrorMemoryAllocation ? VA_E_NOMEM : VA_E_CUDA,                        \
-                        std::string(#call) + ": " + cudaGetErrorString(err__));                             \
-    } while (0)
-
-enum Family { FAM_SCALAR = 0, FAM_GLV_WIDE = 1, FAM_GLV_STREAM = 2, FAM_TAPE = 3 }; // TAPE: scalar kernels compiled at run time for a recorded system
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need)
-    {
-        if (need <= bytes) return VA_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&p, need);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(VA_E_NOMEM, "cudaMalloc(" + std::to_string(need) + " B) failed"); }
-        bytes = need;
-        return VA_OK;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-
+namespace {
+int fail(int code, const std::string &msg) { return va_fail(code, msg); }
 } // namespace
-
-struct va_engine {
-    va_engine_desc desc;
-    VaTableau tab;
-    int family = FAM_SCALAR;
-    VaJitModule *jit = nullptr;
-    int device = 0, sm_count = 0;
-    int cap = 0;
-    cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    // wide family
-    int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
-    bool t8 = false;  // FAM_GLV_WIDE served by va_glv_t8.cu (33..64 species)
-    bool quad = false; // FAM_GLV_WIDE served by va_glv_quad.cu (up to 16 species)
-    int glv_blk = 0;  // doubles per step block of the register-kernel slab
-    bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
-    int ring_flags = 0;
-    bool pairk = false; // FAM_GLV_STREAM served by va_glv_pair.cu (256 species, matrix on chip in a cluster of pair_cl CTAs)
-    int pair_cl = 2;
-    bool pair_seg = false; // ... under the recompute policy: per-CTA state store + segment re-integration
-    int pair_seg_len = 16;
-    int64_t xstore_stride = 0;
-    DevBuf xstore;
-    int64_t slab_stride = 0;
-    DevBuf slab, partial;
-    // scalar family
-    DevBuf ck_t, ck_x, work_counter; // work_counter: 2 x u64, dynamic trajectory / work-item fetch of the persistent grids
-    int64_t arena_traj = 0;
-    // per-trajectory bookkeeping when the caller passes NULL
-    DevBuf own_accept, own_reject, own_status, mu_tmp;
-    // host-mode staging, two slots
-    DevBuf st_x0[2], st_par[2], st_xf[2], st_lam[2], st_mu[2], st_acc[2], st_rej[2], st_sta[2], st_musum;
-    // split API session (va_forward_batch -> va_adjoint_batch / va_get_checkpoints)
-    DevBuf se_x0, se_par, se_xf, se_lam, se_mu, se_acc, se_rej, se_sta;
-    int64_t se_B = 0;
-    double se_ti = 0, se_tf = 0, se_dt0 = 0;
-    std::vector<int32_t> se_accept_host;
-    std::vector<double> se_xf_host;
-    int64_t launches = 0;
-    double last_ms = 0.0;
-    int64_t workspace_bytes = 0, chunk_traj = 0;
-};
 
 namespace {
 
@@ -344,7 +270,10 @@ int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
         const int s = (int)(c & 1);
         const int64_t Bn = std::min(Bc, B - b0);
         // inputs of this slot are free once the kernels of chunk c-2 are done
-        if (c >= 2) VA_CUDA(cudaStreamWaitEvent(e->s_in, e->ev_comp[s], 0));
+        if (c >= 2) {
+            VA_CUDA(cudaStreamWaitEvent(e->s_in, e->ev_comp[s], 0));
+            VA_CUDA(cudaStreamWaitEvent(e->s_in, e->ev_out[s], 0)); // st_lam[s] is seeds in AND dJ/dx(t0) out: drain chunk c-2 first
+        }
         VA_CUDA(cudaMemcpyAsync(e->st_x0[s].p, a->x0 + b0 * n, (size_t)Bn * n * 8, cudaMemcpyHostToDevice, e->s_in));
         VA_CUDA(cudaMemcpyAsync(e->st_par[s].p, a->params + b0 * npar, (size_t)Bn * npar * 8, cudaMemcpyHostToDevice, e->s_in));
         if (!forward_only && a->objective == VA_OBJ_SEED)
@@ -375,8 +304,10 @@ int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
         if (a->status) VA_CUDA(cudaMemcpyAsync(a->status + b0, e->st_sta[s].p, (size_t)Bn * 4, cudaMemcpyDeviceToHost, e->s_out));
         VA_CUDA(cudaEventRecord(e->ev_out[s], e->s_out));
     }
+    if (sum && !forward_only && e->comm) // several GPUs: the one collective of the path, on the sum of this GPU's chunks
+        if (int rc = va_comm_allreduce_sum(e, e->st_musum.as<double>(), (int64_t)nout * npar, e->s_comp)) return rc;
     VA_CUDA(cudaEventRecord(e->ev_t1, e->s_comp));
-    if (sum && !forward_only)
+    if (sum && !forward_only && e->mu_host_writer)
         VA_CUDA(cudaMemcpyAsync(a->mu, e->st_musum.p, (size_t)nout * npar * 8, cudaMemcpyDeviceToHost, e->s_comp));
     VA_CUDA(cudaStreamSynchronize(e->s_in));
     VA_CUDA(cudaStreamSynchronize(e->s_comp));
@@ -390,6 +321,9 @@ int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
 int run_call(va_engine *e, const va_batch_args *a, bool forward_only)
 {
     VA_CUDA(cudaSetDevice(e->device));
+    // a fused call reuses the checkpoint arena / slabs: a split-API session recorded earlier on this engine is gone
+    if (is_glv(e)) { e->se_slab_valid = false; e->se_ck_b = -1; }
+    else e->se_B = 0;
     if (a->mem == VA_MEM_HOST) return run_host(e, a, forward_only);
     cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : e->s_comp;
     DevArgs d;
@@ -399,6 +333,8 @@ int run_call(va_engine *e, const va_batch_args *a, bool forward_only)
     d.forward_only = forward_only;
     VA_CUDA(cudaEventRecord(e->ev_t0, st));
     if (int rc = run_device(e, d, st)) return rc;
+    if (a->reduce == VA_REDUCE_SUM && !forward_only && e->comm)
+        if (int rc = va_comm_allreduce_sum(e, d.mu, (int64_t)e->desc.n_out * e->desc.n_par, st)) return rc;
     VA_CUDA(cudaEventRecord(e->ev_t1, st));
     if (!a->stream) {
         VA_CUDA(cudaStreamSynchronize(st));
@@ -411,11 +347,7 @@ int run_call(va_engine *e, const va_batch_args *a, bool forward_only)
 
 } // namespace
 
-extern "C" {
-
-const char *va_last_error(void) { return g_last_error.c_str(); }
-
-int va_engine_create(const va_engine_desc *desc, va_engine **out)
+int va_single_create(const va_engine_desc *desc, va_engine **out)
 {
     if (!desc || !out) return fail(VA_E_INVALID, "null argument");
     *out = nullptr;
@@ -466,7 +398,7 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
     e->family = family;
     e->device = desc->device;
     e->cap = desc->max_steps > 0 ? desc->max_steps : (family == FAM_GLV_WIDE || family == FAM_GLV_STREAM ? 256 : 2048);
-    auto bail = [&](int code, const std::string &m) { va_engine_destroy(e); return fail(code, m); };
+    auto bail = [&](int code, const std::string &m) { va_single_destroy(e); return fail(code, m); };
     if (cudaSetDevice(e->device) != cudaSuccess) return bail(VA_E_CUDA, "cudaSetDevice failed");
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device);
     bool ok = cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
@@ -591,12 +523,13 @@ int va_engine_create(const va_engine_desc *desc, va_engine **out)
     return VA_OK;
 }
 
-void va_engine_destroy(va_engine *e)
+void va_single_destroy(va_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&e->slab, &e->partial, &e->ck_t, &e->ck_x, &e->work_counter, &e->own_accept, &e->own_reject, &e->own_status, &e->mu_tmp,
+    if (!e->comm_owned_by_head) va_comm_release(e);
+    DevBuf *bufs[] = {&e->slab, &e->partial, &e->xstore, &e->ck_t, &e->ck_x, &e->work_counter, &e->own_accept, &e->own_reject, &e->own_status, &e->mu_tmp,
                       &e->st_musum, &e->se_x0, &e->se_par, &e->se_xf, &e->se_lam, &e->se_mu, &e->se_acc, &e->se_rej, &e->se_sta};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < 2; ++s) {
@@ -615,9 +548,8 @@ void va_engine_destroy(va_engine *e)
     delete e;
 }
 
-int va_engine_get_info(va_engine *e, va_engine_info *info)
+static int single_get_info(va_engine *e, va_engine_info *info)
 {
-    if (!e || !info) return fail(VA_E_INVALID, "null argument");
     std::memset(info, 0, sizeof(*info));
     info->api_version = VA_API_VERSION;
     info->device = e->device;
@@ -636,10 +568,15 @@ int va_engine_get_info(va_engine *e, va_engine_info *info)
     std::snprintf(info->kernel_name, sizeof(info->kernel_name), "%s", kn);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) std::snprintf(info->device_name, sizeof(info->device_name), "%s", prop.name);
+    info->n_devices = 1;
+    info->comm_world = e->comm ? e->comm_world : 0;
+    info->comm_rank = e->comm_rank;
+    info->nccl_version = e->comm ? va_nccl_version() : 0;
+    info->collectives = e->collectives;
     return VA_OK;
 }
 
-int va_forward_adjoint_batch(va_engine *e, const va_batch_args *a)
+int va_single_forward_adjoint(va_engine *e, const va_batch_args *a)
 {
     if (int rc = check_args(e, a, true)) return rc;
     return run_call(e, a, false);
@@ -647,7 +584,7 @@ int va_forward_adjoint_batch(va_engine *e, const va_batch_args *a)
 
 // Split API. The forward call keeps a device-side session (inputs, x(tf), step counts, checkpoints) so that
 // va_adjoint_batch / va_get_checkpoints can serve Driver::GetT/GetTime/GetState and adjointSolve afterwards.
-int va_forward_batch(va_engine *e, const va_batch_args *a)
+int va_single_forward(va_engine *e, const va_batch_args *a)
 {
     if (int rc = check_args(e, a, false)) return rc;
     VA_CUDA(cudaSetDevice(e->device));
@@ -690,16 +627,19 @@ int va_forward_batch(va_engine *e, const va_batch_args *a)
     cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
     e->last_ms = ms;
     e->se_B = B; e->se_ti = a->ti; e->se_tf = a->tf; e->se_dt0 = a->dt0;
+    e->se_slab_valid = is_glv(e); e->se_ck_b = -1;
     return VA_OK;
 }
 
-int va_adjoint_batch(va_engine *e, const va_batch_args *a)
+int va_single_adjoint(va_engine *e, const va_batch_args *a)
 {
     if (!e || !a) return fail(VA_E_INVALID, "null engine or args");
     if (e->se_B <= 0) return fail(VA_E_STATE, "va_adjoint_batch needs a preceding va_forward_batch (runge_kutta) on this engine");
     if (a->batch != e->se_B) return fail(VA_E_INVALID, "batch differs from the preceding va_forward_batch");
     if (!a->lambda || !a->mu) return fail(VA_E_INVALID, "Must call setCostGradients() first!"); // backpropagation.hpp:22-26
     if (a->reduce != VA_REDUCE_NONE && a->reduce != VA_REDUCE_SUM) return fail(VA_E_INVALID, "bad reduce");
+    if (a->objective < VA_OBJ_SEED || a->objective > VA_OBJ_HALF_NORM2) return fail(VA_E_INVALID, "bad objective");
+    if (a->mem != VA_MEM_HOST && a->mem != VA_MEM_DEVICE) return fail(VA_E_INVALID, "bad mem");
     VA_CUDA(cudaSetDevice(e->device));
     const int n = e->desc.n_state, npar = e->desc.n_par, nout = e->desc.n_out;
     const int64_t B = e->se_B;
@@ -741,10 +681,14 @@ int va_adjoint_batch(va_engine *e, const va_batch_args *a)
         d.mu = e->se_mu.as<double>(); d.n_accept = e->se_acc.as<int32_t>(); d.n_reject = e->se_rej.as<int32_t>();
         d.status = e->se_sta.as<int32_t>(); d.mu_accumulate = false; d.forward_only = false;
         if (int rc = run_device(e, d, e->s_comp)) return rc;
+        e->se_ck_b = -1; // slot 0 was reused
     }
+    if (sum && e->comm)
+        if (int rc = va_comm_allreduce_sum(e, e->se_mu.as<double>(), (int64_t)nout * npar, e->s_comp)) return rc;
     VA_CUDA(cudaEventRecord(e->ev_t1, e->s_comp));
     VA_CUDA(cudaMemcpyAsync(a->lambda, e->se_lam.p, (size_t)B * nout * n * 8, out_kind, e->s_comp));
-    VA_CUDA(cudaMemcpyAsync(a->mu, e->se_mu.p, mu_elems * 8, out_kind, e->s_comp));
+    if (!sum || e->mu_host_writer || a->mem == VA_MEM_DEVICE)
+        VA_CUDA(cudaMemcpyAsync(a->mu, e->se_mu.p, mu_elems * 8, out_kind, e->s_comp));
     VA_CUDA(cudaStreamSynchronize(e->s_comp));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1);
@@ -752,13 +696,35 @@ int va_adjoint_batch(va_engine *e, const va_batch_args *a)
     return VA_OK;
 }
 
-int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, double *x, int32_t *count)
+int va_single_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, double *x, int32_t *count)
 {
     if (!e || !count) return fail(VA_E_INVALID, "null argument");
     if (e->se_B <= 0) return fail(VA_E_STATE, "no forward sweep recorded on this engine");
     if (b < 0 || b >= e->se_B) return fail(VA_E_INVALID, "trajectory index out of range");
-    if (is_glv(e) && b >= (e->pairk ? e->grid / e->pair_cl : (int64_t)e->grid * e->tpc))
-        return fail(VA_E_UNSUPPORTED, "the GLV path keeps the checkpoints of the first wave of trajectories only (one per resident slot)");
+    // GLV: a slot's slab holds the LAST trajectory it integrated. Trajectory b sits in slot b only while the batch fitted one
+    // wave of slots and nothing ran since; otherwise it is re-integrated alone (forward only, deterministic) into slot 0.
+    int64_t slot = b;
+    if (is_glv(e)) {
+        const int64_t slots = e->pairk ? e->grid / e->pair_cl : (int64_t)e->grid * e->tpc;
+        if (!(e->se_slab_valid && e->se_B <= slots)) {
+            VA_CUDA(cudaSetDevice(e->device));
+            if (e->se_ck_b != b) {
+                const int n_ = e->desc.n_state, npar_ = e->desc.n_par;
+                if (int rc = e->se_scratch.ensure((size_t)n_ * 8 + 64)) return rc;
+                DevArgs d;
+                d.B = 1; d.x0 = e->se_x0.as<double>() + b * n_; d.params = e->se_par.as<double>() + b * npar_;
+                d.ti = e->se_ti; d.tf = e->se_tf; d.dt0 = e->se_dt0; d.objective = VA_OBJ_SUM; d.reduce = VA_REDUCE_NONE;
+                d.x_final = e->se_scratch.as<double>(); d.lambda = nullptr; d.mu = nullptr;
+                int32_t *ints = reinterpret_cast<int32_t *>(e->se_scratch.as<double>() + n_);
+                d.n_accept = ints; d.n_reject = ints + 1; d.status = ints + 2; d.mu_accumulate = false; d.forward_only = true;
+                if (int rc = run_device(e, d, e->s_comp)) return rc;
+                VA_CUDA(cudaStreamSynchronize(e->s_comp));
+                e->se_slab_valid = false;
+                e->se_ck_b = b;
+            }
+            slot = 0;
+        }
+    }
     const int n = e->desc.n_state;
     const int T = e->se_accept_host[(size_t)b];
     *count = T + 1;
@@ -779,9 +745,9 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
     } else {
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
-        // first wave: trajectory b = slot b, slab 0 (cluster-pair kernel: CTA 2b of pair b)
-        const double *base = e->pair_seg ? e->xstore.as<double>() + b * e->pair_cl * e->xstore_stride
-                                         : e->slab.as<double>() + b * (e->pairk ? e->pair_cl : e->pair) * e->slab_stride;
+        // slab 0 of the slot (cluster-pair kernel: CTA 2 * slot of the pair)
+        const double *base = e->pair_seg ? e->xstore.as<double>() + slot * e->pair_cl * e->xstore_stride
+                                         : e->slab.as<double>() + slot * (e->pairk ? e->pair_cl : e->pair) * e->slab_stride;
         const size_t pitch = e->pair_seg ? (size_t)(8 + 256) * 8 : (size_t)(e->family == FAM_GLV_WIDE || e->ring || e->pairk ? e->glv_blk
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
@@ -791,6 +757,81 @@ int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, dou
         }
     }
     return VA_OK;
+}
+
+extern "C" {
+
+const char *va_last_error(void) { return g_last_error.c_str(); }
+
+int va_engine_create(const va_engine_desc *desc, va_engine **out)
+{
+    if (!desc || !out) return fail(VA_E_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->n_devices < 0 || desc->n_devices > 64) return fail(VA_E_INVALID, "n_devices out of range");
+    if (desc->n_devices > 0 && !desc->devices) return fail(VA_E_INVALID, "n_devices > 0 needs the devices array");
+    if (desc->n_devices > 1) return va_multi_create(desc, out);
+    va_engine_desc d = *desc;
+    if (desc->n_devices == 1) d.device = desc->devices[0];
+    d.n_devices = 0;
+    d.devices = nullptr;
+    return va_single_create(&d, out);
+}
+
+void va_engine_destroy(va_engine *e)
+{
+    if (!e) return;
+    if (!e->members.empty()) va_multi_destroy(e);
+    else va_single_destroy(e);
+}
+
+int va_engine_get_info(va_engine *e, va_engine_info *info)
+{
+    if (!e || !info) return fail(VA_E_INVALID, "null argument");
+    if (e->members.empty()) return single_get_info(e, info);
+    // multi-device engine: the first member describes the kernel; counters are summed, the time is the slowest GPU's
+    single_get_info(e->members[0], info);
+    info->n_devices = (int32_t)e->members.size();
+    info->comm_rank = 0;
+    for (size_t g = 1; g < e->members.size(); ++g) {
+        va_engine_info ig;
+        single_get_info(e->members[g], &ig);
+        info->kernel_launches += ig.kernel_launches;
+        info->workspace_bytes += ig.workspace_bytes;
+        info->chunk_trajectories += ig.chunk_trajectories;
+        info->collectives += ig.collectives;
+        if (ig.last_kernel_ms > info->last_kernel_ms) info->last_kernel_ms = ig.last_kernel_ms;
+    }
+    return VA_OK;
+}
+
+int va_forward_adjoint_batch(va_engine *e, const va_batch_args *a)
+{
+    if (e && !e->members.empty()) return va_multi_call(e, 0, a);
+    return va_single_forward_adjoint(e, a);
+}
+int va_forward_batch(va_engine *e, const va_batch_args *a)
+{
+    if (e && !e->members.empty()) return va_multi_call(e, 1, a);
+    return va_single_forward(e, a);
+}
+int va_adjoint_batch(va_engine *e, const va_batch_args *a)
+{
+    if (e && !e->members.empty()) return va_multi_call(e, 2, a);
+    return va_single_adjoint(e, a);
+}
+int va_forward_adjoint_batch_sharded(va_engine *e, int32_t n_shards, const va_batch_args *shards)
+{
+    if (!e || !shards) return fail(VA_E_INVALID, "null engine or shards");
+    if (e->members.empty()) {
+        if (n_shards != 1) return fail(VA_E_INVALID, "a single-device engine takes exactly one shard");
+        return va_single_forward_adjoint(e, shards);
+    }
+    return va_multi_call_sharded(e, n_shards, shards);
+}
+int va_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double *t, double *x, int32_t *count)
+{
+    if (e && !e->members.empty()) return va_multi_get_checkpoints(e, b, capacity, t, x, count);
+    return va_single_get_checkpoints(e, b, capacity, t, x, count);
 }
 
 int va_tape_compile_check(const char *tape_cuda_src, int32_t stepper, char *log, int32_t log_capacity)
