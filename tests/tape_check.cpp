@@ -69,6 +69,28 @@ struct Zoo {
         d[1] = log10(2.0 + x[0] * x[0]) + log2(1.5 + p[1] * p[1]) + exp2(x[2] * 0.3) + cbrt(1.0 + x[1] * x[1]) + erf(p[0] * x[2]) + fabs(x[0] - 0.9);
         d[2] = atan2(x[0] + p[0], 1.0 + x[1] * x[1]) + fmod(3.7 * x[2] + p[1], 1.3) + fmin(x[0] * x[1], p[0]) + fmax(x[2], x[1] * p[1]) +
                iIf(x[0] * p[1] < x[1] + t, x[0] * x[0], -x[1]) + iIf(x[2] >= p[0], p[1] * x[2], x[2] * x[2] * t);
+        // == != on active values and && || ! != on recorded conditions (AADC ibool.h:81-190)
+        d[0] += iIf((x[0] < 0.5) && !(x[1] > 0.3), p[0] * x[0] * x[1], x[2] * x[2]);
+        d[1] += iIf((x[2] > 0.8) || (x[0] == x[0] * 1.0 && x[1] != x[1] + 1.0 && x[0] > 0.9), x[1] * p[1], -x[0] * x[2]);
+        d[2] += iIf((x[0] < 0.5) != (x[1] < 0.2), p[1] * x[0], p[0] * x[1]) + iIf(true && (x[1] <= 0.27), 1.0 * x[2], 2.0 * x[2]);
+    }
+};
+// coincides with the built-in harmonic oscillator wherever |r| < 5, differs beyond: must stay on the generated path
+struct HO_clamped {
+    template <class T> void operator()(const std::vector<T> &r, std::vector<T> &d, const std::vector<T> &mu, const T) const
+    {
+        using std::fmax;
+        using std::fmin;
+        d[0] = r[1];
+        d[1] = -1.0 * fmax(fmin(r[0], T(5.0)), T(-5.0)) - mu[0] * r[1];
+    }
+};
+struct HO_switch { // same, written with a recorded condition
+    template <class T> void operator()(const std::vector<T> &r, std::vector<T> &d, const std::vector<T> &mu, const T) const
+    {
+        using va::iIf;
+        d[0] = r[1];
+        d[1] = iIf(r[0] < 100.0, -1.0 * r[0], T(-100.0)) - mu[0] * r[1];
     }
 };
 
@@ -86,6 +108,8 @@ int main(int argc, char **argv)
     expect("glv N=64", va::identify(va::record(GLV(), 64, 4160)), va::SYS_GLV);
     expect("glv reordered", va::identify(va::record(GLV_reordered(), 7, 56)), va::SYS_GLV);
     expect("pendulum", va::identify(va::record(Pendulum(), 2, 2)), va::SYS_TAPE);
+    expect("harmonic clamped", va::identify(va::record(HO_clamped(), 2, 1)), va::SYS_TAPE);
+    expect("harmonic switch", va::identify(va::record(HO_switch(), 2, 1)), va::SYS_TAPE);
     // tape evaluation == direct evaluation; generated vjp source is straight-line CUDA
     va::Tape tp = va::record(Pendulum(), 2, 2);
     std::vector<double> x = {0.4, -0.2}, p = {1.3, 0.05}, f(2), g(2), work;

@@ -29,6 +29,7 @@
 #include <cstdlib>
 
 #include "va_glv_common.cuh"
+#include "va_tma.cuh"
 
 #ifndef VA_T8_MINB
 #define VA_T8_MINB 4 // resident CTAs per SM the register allocation is sized for
@@ -63,64 +64,21 @@ static_assert((RT == 8 || RT == 4 || RT == 2) && (NC == 1 || NC == 2 || NC == 4)
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// ---- mbarrier + TMA bulk copy (global -> shared) ------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
+// mbarrier + TMA bulk copy + L2 eviction-policy helpers: va_tma.cuh (one copy for all kernels).
 // L2 residency control. The slabs (592 x ~130 KB of step blocks in flight per GPU) are written, read twice and then
 // overwritten; the parameters (35 GB per pass) stream through once. Without hints the stream evicts the slabs (ncu:
 // 280 KB of DRAM traffic per trajectory against 35 KB of compulsory bytes), so slab accesses carry evict_last and the
 // last read of the parameters evict_first.
-__device__ __forceinline__ uint64_t policy_evict_last()
-{
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_first()
-{
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void st_hint(double *p, double v, uint64_t policy)
-{
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy));
-}
-__device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy)
-{
-    double v;
-    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "T8_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra T8_WAIT_DONE;\n"
-        "bra T8_WAIT_LOOP;\n"
-        "T8_WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+using va_tma::smem_u32;
+using va_tma::mbar_init;
+using va_tma::mbar_expect_tx;
+using va_tma::bulk_g2s;
+using va_tma::policy_evict_last;
+using va_tma::policy_evict_first;
+using va_tma::mbar_wait;
+using va_tma::fence_proxy_async;
+using va_tma::ldg_hint;
+__device__ __forceinline__ void st_hint(double *p, double v, uint64_t policy) { va_tma::st_hint_relaxed(p, v, policy); }
 
 // max over the warp of non-negative doubles (or NaN, which orders above everything): two 32-bit redux operations on
 // the bit pattern instead of five double shuffles + DMNMX

@@ -9,6 +9,12 @@
 // this routine the device reproduces all of them. tests/test_pow_cpu.py compares the HOST build of this file with the
 // system pow() (bit for bit) on millions of arguments; the device executes the same IEEE operations (explicit fma()).
 //
+// Provenance / licence: the algorithm and the numeric tables (va_pow_tables.h, dumped from this image's libm.so.6 by
+// tools/gen_pow_tables.py) originate in the GNU C Library, sysdeps/ieee754/dbl-64/{e_pow.c, e_pow_log_data.c, e_exp_data.c},
+// Copyright (C) Free Software Foundation / Arm Ltd., licensed LGPL-2.1-or-later. This file is a restatement written for
+// this project, not a copy of glibc source; the tables are glibc's data. Redistribution of this file and va_pow_tables.h
+// is therefore under LGPL-2.1-or-later terms.
+//
 // VA_POW_FMA selects the variant glibc picks at run time on an FMA-capable x86-64 (ifunc __pow_fma); without it the
 // Dekker-split variant of the generic build is used.
 #pragma once

@@ -89,4 +89,19 @@ __device__ __forceinline__ double ld_hint(const double *p, uint64_t policy)
     return v;
 }
 
+// the same store without the compiler-level memory clobber: for checkpoint stores inside register-tuned loops, where the
+// clobber would act as a scheduling wall (ordering towards the later TMA reads comes from a barrier + fence_proxy_async)
+__device__ __forceinline__ void st_hint_relaxed(double *p, double v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy));
+}
+// read-only (non-coherent) load with an eviction policy: parameters that stream through once
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy)
+{
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 } // namespace va_tma

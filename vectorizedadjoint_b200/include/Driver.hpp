@@ -139,7 +139,8 @@ void recordDriverRHSFunction(Driver &driver, System system)
     driver.p_aad_data = std::move(data);
 }
 
-// Sets the derivatives of each component of the cost function w.r.t. to the ODE solution and w.r.t. the parameters
+// Hands the driver the caller's seed vectors: lambda[o] = dJ_o/dx(tf) on entry, mu[o] = the accumulator dJ_o/dalpha is added to
+// (borrowed pointers, reference Driver.hpp:103-114)
 inline void setCostGradients(Driver &driver, std::vector<std::vector<double>> &lambda, std::vector<std::vector<double>> &mu)
 {
     assert((int)lambda.size() == driver.GetNout());

@@ -64,8 +64,8 @@ std::vector<std::vector<double>> computeSensitivityMatrix(Driver &driver, const 
 
 } // namespace detail
 
-// Computes the adjoints of the cost functions (the total derivatives of the cost function with respect to the initial
-// conditions and with respect to the parameters)
+// Reverse sweep for every cost function registered with setCostGradients: on return lambda[o] = dJ_o/dx(t0) and
+// mu[o] += dJ_o/dalpha
 template <class State>
 void adjointSolve(Driver &driver, const State &parameters)
 {
@@ -80,7 +80,7 @@ void adjointSolve(Driver &driver, const State &parameters)
     }
 }
 
-// Computes the sensitivity matrix of the ODE system (one reverse sweep per state component in the reference; here all
+// d x(tf) / d alpha as an Nin x Npar matrix (one reverse sweep per state component in the reference; here all
 // components are seeds of one batched reverse sweep)
 template <class State>
 auto computeSensitivityMatrix(Driver &driver, const State &parameters)

@@ -83,7 +83,7 @@ size_t run_forward(int stepper_id, int adaptive, double eps_abs, double eps_rel,
     return static_cast<size_t>(n_accept);
 }
 
-// for non-controlled steppers
+// tag dispatch: fixed-step steppers (stepper_tag)
 template <class Stepper, class System, class State, class Time, class Observer>
 size_t runge_kutta(Stepper, System system, State &start_state, const State &alphas, Time start_time, const Time end_time, Time dt,
                    Driver &driver, Observer observer, odeint::stepper_tag)
@@ -91,7 +91,7 @@ size_t runge_kutta(Stepper, System system, State &start_state, const State &alph
     return run_forward(Stepper::va_stepper_id, 0, 0.0, 0.0, system, start_state, alphas, start_time, end_time, dt, driver, observer);
 }
 
-// For controlled steppers
+// tag dispatch: make_controlled<...> steppers (controlled_stepper_tag)
 template <class Stepper, class System, class State, class Time, class Observer>
 size_t runge_kutta(Stepper stepper, System system, State &start_state, const State &alphas, Time start_time, const Time end_time, Time dt,
                    Driver &driver, Observer observer, odeint::controlled_stepper_tag)
@@ -102,7 +102,7 @@ size_t runge_kutta(Stepper stepper, System system, State &start_state, const Sta
 
 } // namespace detail_runge_kutta
 
-// With observer
+// public entry, observer called with every accepted (x, t)
 template <class Stepper, class System, class State, class Time, class Observer>
 size_t runge_kutta(Stepper stepper, System system, State &start_state, const State &alphas, Time start_time, const Time end_time, Time dt,
                    Driver &driver, Observer observer)
@@ -112,7 +112,7 @@ size_t runge_kutta(Stepper stepper, System system, State &start_state, const Sta
                                            stepper_category());
 }
 
-// Without observer
+// public entry, no observer
 template <class Stepper, class System, class State, class Time>
 size_t runge_kutta(Stepper stepper, System system, State &start_state, const State &alphas, Time start_time, const Time end_time, Time dt,
                    Driver &driver)

@@ -26,7 +26,9 @@ enum OpCode : uint8_t { OP_INPUT_X, OP_INPUT_P, OP_INPUT_T, OP_CONST, OP_ADD, OP
                         OP_TAN, OP_ASIN, OP_ACOS, OP_ATAN, OP_SINH, OP_COSH, OP_LOG10, OP_LOG2, OP_EXP2, OP_CBRT, OP_ERF, OP_FABS,
                         OP_ATAN2, OP_FMOD, OP_FMIN, OP_FMAX,
                         OP_LT, OP_LE, OP_GT, OP_GE, // comparisons: value 1.0 / 0.0, no derivative
-                        OP_SELECT };                // s ? a : b  (iIf)
+                        OP_SELECT,                  // s ? a : b  (iIf)
+                        OP_EQ, OP_NE,               // == != on active values (ibool.h:172-190)
+                        OP_AND, OP_OR, OP_XOR, OP_NOT }; // && || != ! on recorded conditions (ibool.h:81-127)
 
 struct Node {
     OpCode op;
@@ -93,6 +95,12 @@ class Tape
             case OP_GT: v = work[n.a] > work[n.b] ? 1.0 : 0.0; break;
             case OP_GE: v = work[n.a] >= work[n.b] ? 1.0 : 0.0; break;
             case OP_SELECT: v = work[n.s] != 0.0 ? work[n.a] : work[n.b]; break;
+            case OP_EQ: v = work[n.a] == work[n.b] ? 1.0 : 0.0; break;
+            case OP_NE: v = work[n.a] != work[n.b] ? 1.0 : 0.0; break;
+            case OP_AND: v = (work[n.a] != 0.0 && work[n.b] != 0.0) ? 1.0 : 0.0; break;
+            case OP_OR: v = (work[n.a] != 0.0 || work[n.b] != 0.0) ? 1.0 : 0.0; break;
+            case OP_XOR: v = ((work[n.a] != 0.0) != (work[n.b] != 0.0)) ? 1.0 : 0.0; break;
+            case OP_NOT: v = work[n.a] != 0.0 ? 0.0 : 1.0; break;
             }
             work[k] = v;
         }
@@ -222,7 +230,36 @@ VA_TAPE_COMPARE(<, OP_LT)
 VA_TAPE_COMPARE(<=, OP_LE)
 VA_TAPE_COMPARE(>, OP_GT)
 VA_TAPE_COMPARE(>=, OP_GE)
+VA_TAPE_COMPARE(==, OP_EQ)
+VA_TAPE_COMPARE(!=, OP_NE)
 #undef VA_TAPE_COMPARE
+// Logic on recorded conditions (AADC ibool.h:81-127: && and || -- there inside namespace aadcBoolOps --, != as exclusive or,
+// and !). A passive operand (plain bool) becomes a constant node. Both operands are always evaluated: a recorded condition
+// cannot short-circuit.
+inline int32_t abool_id(const abool &c) { return c.node >= 0 ? c.node : active_tape()->push(OP_CONST, -1, -1, c.val ? 1.0 : 0.0); }
+#define VA_TAPE_LOGIC(SYM, OP, EXPR)                                                                   \
+    inline abool operator SYM(const abool &a, const abool &b)                                          \
+    {                                                                                                  \
+        abool r(EXPR);                                                                                 \
+        if (active_tape() && (a.node >= 0 || b.node >= 0)) {                                           \
+            const int32_t ia = abool_id(a), ib = abool_id(b);                                          \
+            r.node = active_tape()->push(OP, ia, ib);                                                  \
+        }                                                                                              \
+        return r;                                                                                      \
+    }                                                                                                  \
+    inline abool operator SYM(bool a, const abool &b) { return abool(a) SYM b; }                       \
+    inline abool operator SYM(const abool &a, bool b) { return a SYM abool(b); }
+VA_TAPE_LOGIC(&&, OP_AND, a.val && b.val)
+VA_TAPE_LOGIC(||, OP_OR, a.val || b.val)
+VA_TAPE_LOGIC(!=, OP_XOR, a.val != b.val)
+#undef VA_TAPE_LOGIC
+inline abool operator!(const abool &a)
+{
+    abool r(!a.val);
+    if (active_tape() && a.node >= 0) r.node = active_tape()->push(OP_NOT, a.node);
+    return r;
+}
+namespace aadcBoolOps {} // source compatibility: `using namespace aadcBoolOps;` in a functor written for AADC is harmless here
 inline adouble iIf(const abool &c, const adouble &a, const adouble &b)
 {
     if (c.node < 0) return c.val ? a : b; // condition on passive values: an ordinary branch
@@ -278,11 +315,21 @@ inline void builtin_rhs(int kind, int n, const double *x, const double *p, doubl
     }
 }
 
-// Which built-in functor does the tape compute? Decided numerically: the tape is evaluated at a few pseudo-random
-// points and compared with the built-in formulas (robust against a different operation order in the user's functor).
+// Which built-in functor does the tape compute? A tape is mapped to a hand-written device functor only when that is PROVABLY
+// the same function: (1) structurally, the tape must be a polynomial in (x, p, t) -- inputs, constants, + - * and negation
+// only; any division, elementary function, min / max / fabs / fmod, comparison or select node keeps it on the generated
+// (SYS_TAPE) path, so a branchy functor that merely coincides with a built-in at the sample points is never swapped;
+// (2) numerically, the polynomial must agree with the built-in formula (also a polynomial, total degree <= 4) at 12
+// pseudo-random points spread over four decades -- two different polynomials of that degree agree at a random point with
+// probability zero (Schwartz-Zippel). Robust against a different operation order in the user's functor.
 inline int identify(const Tape &tape)
 {
     const int n = tape.n_x, np = tape.n_p;
+    for (const Node &nd : tape.nodes)
+        switch (nd.op) {
+        case OP_INPUT_X: case OP_INPUT_P: case OP_INPUT_T: case OP_CONST: case OP_ADD: case OP_SUB: case OP_MUL: case OP_NEG: break;
+        default: return SYS_TAPE;
+        }
     std::vector<int> candidates;
     if (n == 2 && np == 1) { candidates.push_back(SYS_HARMONIC); candidates.push_back(SYS_VANDERPOL); }
     if (np == n * n + n) candidates.push_back(SYS_GLV);
@@ -290,13 +337,16 @@ inline int identify(const Tape &tape)
     for (int kind : candidates) {
         bool same = true;
         uint64_t s = 0x243F6A8885A308D3ULL;
-        for (int trial = 0; trial < 3 && same; ++trial) {
+        for (int trial = 0; trial < 12 && same; ++trial) {
             auto u = [&]() { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(s >> 11) * 0x1.0p-53 * 2.0 - 1.0; };
-            for (auto &v : x) v = u();
-            for (auto &v : p) v = 2.0 * u();
-            tape.eval(x.data(), p.data(), 0.37 * trial, f.data(), work);
+            const double sx = std::pow(10.0, (trial % 4) - 2), sp = std::pow(10.0, ((trial / 4) % 3) - 1); // 1e-2..10, 0.1..10
+            for (auto &v : x) v = sx * u();
+            for (auto &v : p) v = sp * 2.0 * u();
+            tape.eval(x.data(), p.data(), 0.37 * trial - 1.5, f.data(), work);
             builtin_rhs(kind, n, x.data(), p.data(), g.data());
-            for (int i = 0; i < n; ++i) same = same && std::fabs(f[i] - g[i]) <= 1e-12 * (1.0 + std::fabs(g[i]));
+            double scale = 0.0;
+            for (int i = 0; i < n; ++i) scale = std::fmax(scale, std::fabs(g[i]));
+            for (int i = 0; i < n; ++i) same = same && std::fabs(f[i] - g[i]) <= 1e-12 * (scale + std::fabs(g[i])) + 1e-300;
         }
         if (same) return kind;
     }
@@ -354,6 +404,12 @@ inline std::string Tape::cuda_source(const std::string &name) const
             case OP_GT: o << "(" << v(n.a) << " > " << v(n.b) << " ? 1.0 : 0.0)"; break;
             case OP_GE: o << "(" << v(n.a) << " >= " << v(n.b) << " ? 1.0 : 0.0)"; break;
             case OP_SELECT: o << "(" << v(n.s) << " != 0.0 ? " << v(n.a) << " : " << v(n.b) << ")"; break;
+            case OP_EQ: o << "(" << v(n.a) << " == " << v(n.b) << " ? 1.0 : 0.0)"; break;
+            case OP_NE: o << "(" << v(n.a) << " != " << v(n.b) << " ? 1.0 : 0.0)"; break;
+            case OP_AND: o << "((" << v(n.a) << " != 0.0 && " << v(n.b) << " != 0.0) ? 1.0 : 0.0)"; break;
+            case OP_OR: o << "((" << v(n.a) << " != 0.0 || " << v(n.b) << " != 0.0) ? 1.0 : 0.0)"; break;
+            case OP_XOR: o << "(((" << v(n.a) << " != 0.0) != (" << v(n.b) << " != 0.0)) ? 1.0 : 0.0)"; break;
+            case OP_NOT: o << "(" << v(n.a) << " != 0.0 ? 0.0 : 1.0)"; break;
             }
             o << ";\n";
         }
