@@ -43,6 +43,21 @@ def assert_close(a, b, rtol=RTOL, what=""):
     assert err <= rtol, f"{what}: relative error {err:.3e} > {rtol:.1e}"
 
 
+def assert_flips_bounded(r, o, same, tol):
+    """north_star: 'accepted-step counts must match per trajectory except documented rounding-induced accept/reject flips'.
+    A flipped trajectory took a different (equally valid) step sequence: it is a different discretisation of the same ODE, so it
+    must still agree with the oracle's to the order of the integration tolerance -- bounded here at 10 * tol relative (never
+    silently dropped from the comparison)."""
+    flipped = ~same
+    if not flipped.any():
+        return
+    bound = 10.0 * max(tol, 1e-12)
+    assert np.abs(r["n_accept"][flipped] - o["n_accept"][flipped]).max() <= 2, "a flip changes the step count by one or two"
+    assert_close(r["x_final"][flipped], o["x_final"][flipped], rtol=bound, what="x(tf), flipped trajectories")
+    assert_close(r["lam"][flipped, 0], o["lam"][flipped], rtol=bound, what="lambda, flipped trajectories")
+    assert_close(r["mu"][flipped, 0], o["mu"][flipped], rtol=bound, what="mu, flipped trajectories")
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # small systems, thread per trajectory
 # ---------------------------------------------------------------------------------------------------------------------
@@ -227,12 +242,12 @@ def test_glv_batch_vs_oracle(va, N, stepper, adaptive, tol, tf, dt0):
         r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
         s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
     assert (r["status"] == 0).all()
-    same = r["n_accept"] == o["n_accept"]
+    same = (r["n_accept"] == o["n_accept"]) & (r["n_reject"] == o["n_reject"])
     assert same.mean() >= 0.99, f"{(~same).sum()} of {B} trajectories differ in accepted steps"
-    np.testing.assert_array_equal(r["n_reject"][same], o["n_reject"][same])
     assert_close(r["x_final"][same], o["x_final"][same], what="x(tf)")
     assert_close(r["lam"][same, 0], o["lam"][same], what="lambda")
     assert_close(r["mu"][same, 0], o["mu"][same], what="mu")
+    assert_flips_bounded(r, o, same, tol)
     # summed-objective mode (per-CTA register accumulation + deterministic reduction) == sum of per-trajectory gradients
     assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
     np.testing.assert_array_equal(s["lam"], r["lam"])
@@ -287,6 +302,56 @@ def test_glv_finite_difference_cross_check(va):
     for m, k in enumerate(ks):
         fd = (J[2 * m] - J[2 * m + 1]) / (2 * h)
         assert abs(fd - base["mu"][0, 0, k]) <= 1e-7 * abs(fd) + 5e-9, (k, fd, base["mu"][0, 0, k])  # FD noise ~ eps/h
+
+
+def test_glv64_flip_census_against_the_oracle(va):
+    """4096 seeded parameter sets of the headline workload against the oracle, EVERY trajectory compared: same accept/reject
+    sequence -> 1e-8 relative (observed ~1e-12); flipped -> 10 * tol. The flip count is printed (pytest -s) and bounded."""
+    N, B, tol = 64, 4096, 1e-8
+    p = oracle.synth_params(oracle.SYS_GLV, N, 1234, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, tol, tol, x0, p, 0.0, 10.0, 1e-3, objective=oracle.OBJ_SUM,
+                               threads=os.cpu_count() or 1)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, tol, tol) as e:
+        r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+    assert (r["status"] == 0).all()
+    same = (r["n_accept"] == o["n_accept"]) & (r["n_reject"] == o["n_reject"])
+    print(f"flip census N=64 tol=1e-8: {(~same).sum()} of {B} trajectories took a different accept/reject sequence")
+    assert (~same).mean() <= 0.002
+    assert_close(r["x_final"][same], o["x_final"][same], what="x(tf)")
+    assert_close(r["lam"][same, 0], o["lam"][same], what="lambda")
+    assert_close(r["mu"][same, 0], o["mu"][same], what="mu")
+    assert_flips_bounded(r, o, same, tol)
+
+
+@pytest.mark.parametrize("N", [16, 64, 100])
+@pytest.mark.parametrize("stepper,adaptive,tol,tf,dt0,max_steps", [
+    (0, False, 0.0, 1.0, 0.01, 128),      # euler, fixed step (reference ButcherTable.hpp:50-65)
+    (4, True, 1e-8, 10.0, 1e-3, 0),       # fehlberg78 controlled, 13 stages (ButcherTable.hpp:191-246)
+    (4, False, 0.0, 1.0, 0.02, 64),       # error steppers used un-controlled: the stepper_tag loop (detail/runge_kutta.hpp:38-72)
+    (2, False, 0.0, 1.0, 0.02, 64),
+    (3, False, 0.0, 1.0, 0.02, 64),
+    (4, True, 1e-5, 10.0, 1e-3, 0)])
+def test_glv_every_reference_tableau_on_every_size(va, N, stepper, adaptive, tol, tf, dt0, max_steps):
+    """The reference runs any of its tableaux on any system; so does the GLV path (streamed-matrix family for the steppers the
+    register kernels do not specialise)."""
+    B = 40
+    p = oracle.synth_params(oracle.SYS_GLV, N, 777, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_SUM, threads=8)
+    for policy in (va.CKPT_STORE_STAGES, va.CKPT_RECOMPUTE):
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, max_steps=max_steps, ckpt_policy=policy) as e:
+            r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM)
+            s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+            assert e.info()["kernel_name"] == "k_glv_stream"
+        assert (r["status"] == 0).all()
+        same = (r["n_accept"] == o["n_accept"]) & (r["n_reject"] == o["n_reject"])
+        assert same.all() if not adaptive else same.mean() >= 0.95
+        assert_close(r["x_final"][same], o["x_final"][same], what="x(tf)")
+        assert_close(r["lam"][same, 0], o["lam"][same], what="lambda")
+        assert_close(r["mu"][same, 0], o["mu"][same], what="mu")
+        assert_flips_bounded(r, o, same, tol)
+        assert_close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True), rtol=1e-11, what="mu sum")
 
 
 def test_glv_full_size_properties(va):

@@ -374,7 +374,7 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
         else if (va_glv_stream_supported(desc->n_state, desc->stepper, desc->adaptive))
             family = FAM_GLV_STREAM; // any N: matrix streamed from L2/HBM
         else
-            return fail(VA_E_UNSUPPORTED, "GLV: supported steppers are rk4 (fixed step), cash_karp54 and dopri5 (controlled)");
+            return fail(VA_E_UNSUPPORTED, "GLV: this species count / stepper does not fit the streamed kernel's shared memory (euler, rk4 fixed step; cash_karp54, dopri5, fehlberg78 fixed step or controlled)");
         break;
     case VA_SYS_TAPE:
         if (!desc->tape_cuda_src) return fail(VA_E_INVALID, "VA_SYS_TAPE needs tape_cuda_src (va::Tape::cuda_source(\"VaUserSys\"))");

@@ -68,6 +68,48 @@ struct TabDOPRI5 {
     }
 };
 
+// explicit Euler (reference lib/include/ButcherTable.hpp:50-65): one stage, b = (1)
+struct TabEuler {
+    static constexpr int S = 1, SADJ = 1, STEPPER_ORDER = 1, ERROR_ORDER = 0;
+    static constexpr bool FSAL = false, HAS_ERR = false;
+    __host__ __device__ static constexpr double a(int, int) { return 0.0; }
+    __host__ __device__ static constexpr double b(int) { return 1.0; }
+    __host__ __device__ static constexpr double db(int) { return 0.0; }
+};
+// Fehlberg 7(8), 13 stages (reference lib/include/ButcherTable.hpp:191-246; odeint rk78_coefficients_*): orders 8 / 8 / 7
+struct TabRKF78 {
+    static constexpr int S = 13, SADJ = 13, STEPPER_ORDER = 8, ERROR_ORDER = 7;
+    static constexpr bool FSAL = false, HAS_ERR = true;
+    __host__ __device__ static constexpr double a(int m, int j)
+    {
+        constexpr double t[13][12] = {
+            {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+            {2.0 / 27, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+            {1.0 / 36, 1.0 / 12, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+            {1.0 / 24, 0, 1.0 / 8, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+            {5.0 / 12, 0, -25.0 / 16, 25.0 / 16, 0, 0, 0, 0, 0, 0, 0, 0},
+            {1.0 / 20, 0, 0, 1.0 / 4, 1.0 / 5, 0, 0, 0, 0, 0, 0, 0},
+            {-25.0 / 108, 0, 0, 125.0 / 108, -65.0 / 27, 125.0 / 54, 0, 0, 0, 0, 0, 0},
+            {31.0 / 300, 0, 0, 0, 61.0 / 225, -2.0 / 9, 13.0 / 900, 0, 0, 0, 0, 0},
+            {2.0, 0, 0, -53.0 / 6, 704.0 / 45, -107.0 / 9, 67.0 / 90, 3.0, 0, 0, 0, 0},
+            {-91.0 / 108, 0, 0, 23.0 / 108, -976.0 / 135, 311.0 / 54, -19.0 / 60, 17.0 / 6, -1.0 / 12, 0, 0, 0},
+            {2383.0 / 4100, 0, 0, -341.0 / 164, 4496.0 / 1025, -301.0 / 82, 2133.0 / 4100, 45.0 / 82, 45.0 / 164, 18.0 / 41, 0, 0},
+            {3.0 / 205, 0, 0, 0, 0, -6.0 / 41, -3.0 / 205, -3.0 / 41, 3.0 / 41, 6.0 / 41, 0, 0},
+            {-1777.0 / 4100, 0, 0, -341.0 / 164, 4496.0 / 1025, -289.0 / 82, 2193.0 / 4100, 51.0 / 82, 33.0 / 164, 12.0 / 41, 0, 1.0}};
+        return t[m][j];
+    }
+    __host__ __device__ static constexpr double b(int j)
+    {
+        constexpr double t[13] = {0, 0, 0, 0, 0, 34.0 / 105, 9.0 / 35, 9.0 / 35, 9.0 / 280, 9.0 / 280, 0, 41.0 / 840, 41.0 / 840};
+        return t[j];
+    }
+    __host__ __device__ static constexpr double db(int j)
+    {
+        constexpr double t[13] = {0.0 - 41.0 / 840, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0 - 41.0 / 840, 41.0 / 840, 41.0 / 840};
+        return t[j];
+    }
+};
+
 // e^(-1/P) for e > 0: float seed + Newton on y^-P = e (quadratic), accurate to a few ulp; replaces pow() in
 // odeint's default_step_adjuster on this path (all 256 threads evaluate it redundantly, so it has to be short).
 template <int P>

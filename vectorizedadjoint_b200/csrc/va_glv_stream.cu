@@ -277,9 +277,11 @@ cudaError_t launch(const VaGlvWideArgs &a, cudaStream_t st, size_t smem)
 int stages_of(int stepper, int *sadj)
 {
     switch (stepper) {
+    case VA_RK_EULER: *sadj = TabEuler::SADJ; return TabEuler::S;
     case VA_RK_RK4: *sadj = TabRK4::SADJ; return TabRK4::S;
     case VA_RK_CK54: *sadj = TabCK54::SADJ; return TabCK54::S;
     case VA_RK_DOPRI5: *sadj = TabDOPRI5::SADJ; return TabDOPRI5::S;
+    case VA_RK_RKF78: *sadj = TabRKF78::SADJ; return TabRKF78::S;
     }
     *sadj = 0;
     return 0;
@@ -297,10 +299,11 @@ size_t va_glv_stream_smem(int n, int stepper, int recompute)
 bool va_glv_stream_supported(int n, int stepper, int adaptive)
 {
     if (n < 1) return false;
-    if (va_glv_stream_smem(n, stepper, 1) > 200 * 1024) return false; // vectors must fit shared memory (N up to ~800)
-    if (stepper == VA_RK_RK4) return !adaptive;
-    if (stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5) return adaptive != 0;
-    return false;
+    if (va_glv_stream_smem(n, stepper, 1) > 200 * 1024) return false; // vectors must fit shared memory (cash_karp54: N up to ~800)
+    // every tableau the reference's ButcherTable knows (ButcherTable.hpp:50-246) + dopri5; error steppers run controlled
+    // (make_controlled<...>) or fixed-step (the stepper_tag overload, detail/runge_kutta.hpp:38-72, which ignores the estimate)
+    if (stepper == VA_RK_EULER || stepper == VA_RK_RK4) return !adaptive;
+    return stepper == VA_RK_CK54 || stepper == VA_RK_DOPRI5 || stepper == VA_RK_RKF78;
 }
 
 int va_glv_stream_block_doubles(int n, int stepper, int recompute)
@@ -315,9 +318,11 @@ cudaError_t va_glv_stream_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t s
     if (a.B <= 0) return cudaSuccess;
     const size_t smem = va_glv_stream_smem(a.n, a.stepper, a.recompute);
     switch (a.stepper) {
+    case VA_RK_EULER: return launch<TabEuler, false>(a, st, smem);
     case VA_RK_RK4: return launch<TabRK4, false>(a, st, smem);
-    case VA_RK_CK54: return launch<TabCK54, true>(a, st, smem);
-    case VA_RK_DOPRI5: return launch<TabDOPRI5, true>(a, st, smem);
+    case VA_RK_CK54: return a.adaptive ? launch<TabCK54, true>(a, st, smem) : launch<TabCK54, false>(a, st, smem);
+    case VA_RK_DOPRI5: return a.adaptive ? launch<TabDOPRI5, true>(a, st, smem) : launch<TabDOPRI5, false>(a, st, smem);
+    case VA_RK_RKF78: return a.adaptive ? launch<TabRKF78, true>(a, st, smem) : launch<TabRKF78, false>(a, st, smem);
     }
     return cudaErrorInvalidValue;
 }
