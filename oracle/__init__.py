@@ -24,6 +24,9 @@ _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_ip = ctypes.POINTER(ctypes.c_int32)
 
 SYS_HARMONIC, SYS_VANDERPOL, SYS_GLV = 0, 1, 2
+# reference back-end only (recorded example systems of vectorizedadjoint_b200/examples/tape_systems.hpp; n = 2, npar = 3)
+SYS_PENDULUM, SYS_SWITCHED, SYS_PENDULUM_AUTONOMOUS, SYS_SWITCHED_AUTONOMOUS, SYS_HARVESTED_GLV = 3, 4, 5, 6, 7
+RK_CK54_FIXED, RK_RKF78_FIXED = 12, 14  # reference back-end: error steppers through the fixed-step loop
 RK_EULER, RK_RK4, RK_CK54, RK_DOPRI5, RK_RKF78 = 0, 1, 2, 3, 4
 OBJ_SEED, OBJ_SUM, OBJ_HALF_NORM2 = 0, 1, 2
 
@@ -85,7 +88,7 @@ def ref_lib():
 
 
 def npar_of(sys: int, n: int) -> int:
-    return n * n + n if sys == SYS_GLV else 1
+    return n * n + n if sys in (SYS_GLV, SYS_HARVESTED_GLV) else 3 if sys >= SYS_PENDULUM else 1
 
 
 def synth_params(sys: int, n: int, seed: int, b0: int, B: int) -> np.ndarray:

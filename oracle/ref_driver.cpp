@@ -15,6 +15,9 @@
 #include <boost/numeric/odeint.hpp>
 
 #include "lib.hpp" // the reference's umbrella header (found through -I/root/reference/lib/include)
+#include <aadc/ibool.h> // comparisons / iIf / max on the reference's active type (used by the recorded example systems)
+
+#include "tape_systems.hpp" // vectorizedadjoint_b200/examples: the two systems the product serves through its tape -> CUDA path
 
 using namespace vectorizedadjoint;
 namespace odeint = boost::numeric::odeint;
@@ -51,6 +54,11 @@ struct GlvSys {
         }
     }
 };
+
+// autonomous variants of the two recorded example systems: the reference's reverse sweep evaluates every stage at t_n
+// (detail/backpropagation.hpp:48,127), so only autonomous systems give reference gradients that are right
+struct PendulumAutonomous : tape_systems::DrivenPendulum { PendulumAutonomous() { omega = 0.0; } };
+struct SwitchedAutonomous : tape_systems::Switched { SwitchedAutonomous() { tscale = 0.0; } };
 
 std::mutex g_record_mutex;
 
@@ -117,6 +125,9 @@ int dispatch_stepper(int stepper, const Job &j)
     case 1: run_range<odeint::runge_kutta4<S>, System, false>(j); return 0;
     case 2: run_range<odeint::runge_kutta_cash_karp54<S>, System, true>(j); return 0;
     case 4: run_range<odeint::runge_kutta_fehlberg78<S>, System, true>(j); return 0;
+    // error steppers used un-controlled: the stepper_tag overload (detail/runge_kutta.hpp:38-72) takes them through tag inheritance
+    case 12: run_range<odeint::runge_kutta_cash_karp54<S>, System, false>(j); return 0;
+    case 14: run_range<odeint::runge_kutta_fehlberg78<S>, System, false>(j); return 0;
     default: return -1; // dopri5 is not supported by the reference's ButcherTable (ButcherTable.hpp:247-250)
     }
 }
@@ -125,7 +136,9 @@ int dispatch_stepper(int stepper, const Job &j)
 
 extern "C" {
 
-// sys: 0 harmonic, 1 van der pol, 2 GLV.  stepper: 0 euler, 1 rk4 (fixed step), 2 ck54, 4 rkf78 (adaptive).
+// sys: 0 harmonic, 1 van der pol, 2 GLV, 3 driven pendulum, 4 switched oscillator (tape_systems.hpp; n = 2, npar = 3),
+//      5 / 6 the same two made autonomous (omega = 0 / tscale = 0), 7 harvested Lotka-Volterra (npar = n*n + n).
+// stepper: 0 euler, 1 rk4 (fixed step), 2 ck54, 4 rkf78 (adaptive), 12 ck54, 14 rkf78 (fixed step).
 // objective: 0 seeds given in lambda_inout, 1 seed = 1 (J = sum x_i(tf)), 2 seed = x(tf) (J = |x(tf)|^2/2).
 // lambda_inout [B][nout][n], mu_out [B][nout][npar] (overwritten), x_final [B][n], n_accept [B] or NULL.
 int va_ref_forward_adjoint_batch(int sys, int n, int npar, int nout, int stepper, double eps_abs, double eps_rel, long B,
@@ -146,6 +159,11 @@ int va_ref_forward_adjoint_batch(int sys, int n, int npar, int nout, int stepper
         case 0: rc[k] = dispatch_stepper<HarmonicSys>(stepper, jobs[k]); break;
         case 1: rc[k] = dispatch_stepper<VanDerPolSys>(stepper, jobs[k]); break;
         case 2: rc[k] = dispatch_stepper<GlvSys>(stepper, jobs[k]); break;
+        case 3: rc[k] = dispatch_stepper<tape_systems::DrivenPendulum>(stepper, jobs[k]); break;
+        case 4: rc[k] = dispatch_stepper<tape_systems::Switched>(stepper, jobs[k]); break;
+        case 5: rc[k] = dispatch_stepper<PendulumAutonomous>(stepper, jobs[k]); break;
+        case 6: rc[k] = dispatch_stepper<SwitchedAutonomous>(stepper, jobs[k]); break;
+        case 7: rc[k] = dispatch_stepper<tape_systems::HarvestedLotkaVolterra>(stepper, jobs[k]); break;
         default: rc[k] = -2;
         }
     };

@@ -121,6 +121,68 @@ def main():
     arrays["ho_sweep_x_final"] = res["x_final"]
     arrays["ho_sweep_lam"] = res["lam"][:, 0]
     arrays["ho_sweep_mu"] = res["mu"][:, 0]
+    # 4. GLV through the steppers the first fixture set did not cover: euler (fixed), fehlberg78 (controlled), and error
+    #    steppers used un-controlled (the reference's stepper_tag loop takes them through tag inheritance)
+    N, B = 16, 4
+    p = oracle.synth_params(oracle.SYS_GLV, N, 777, 0, B)
+    x0s = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    for name, st, tol, tf, dt in (("euler_fixed", oracle.RK_EULER, 0.0, 1.0, 0.01), ("rkf78_1e-8", oracle.RK_RKF78, 1e-8, 10.0, 1e-3),
+                                  ("ck54_fixed", oracle.RK_CK54_FIXED, 0.0, 1.0, 0.02), ("rkf78_fixed", oracle.RK_RKF78_FIXED, 0.0, 1.0, 0.02)):
+        res = oracle.reference_forward_adjoint(oracle.SYS_GLV, N, st, tol, tol, x0s, p, 0.0, tf, dt, objective=oracle.OBJ_SUM)
+        k = f"glv_N{N}_{name}"
+        arrays[k + "_steps"] = res["n_accept"]
+        arrays[k + "_x_final"] = res["x_final"]
+        arrays[k + "_lam"] = res["lam"][:, 0]
+        arrays[k + "_mu"] = res["mu"][:, 0]
+    # 5. GLV N = 256 (BASELINE config 5), two parameter sets; the 65792-entry gradients are stored as the growth-rate block,
+    #    every 16th matrix entry, and the sum (526 KB each in full)
+    N, B = 256, 2
+    p = oracle.synth_params(oracle.SYS_GLV, N, 1234, 0, B)
+    x0s = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    res = oracle.reference_forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, 1e-8, 1e-8, x0s, p, 0.0, 10.0, 1e-3, objective=oracle.OBJ_SUM, threads=2)
+    k = "glv_N256_ck54_1e-8"
+    arrays[k + "_steps"] = res["n_accept"]
+    arrays[k + "_x_final"] = res["x_final"]
+    arrays[k + "_lam"] = res["lam"][:, 0]
+    arrays[k + "_mu_r"] = res["mu"][:, 0, :N]
+    arrays[k + "_mu_A_every16"] = res["mu"][:, 0, N::16]
+    arrays[k + "_mu_sum"] = res["mu"][:, 0].sum(axis=1)
+    # 6. the recorded (tape path) example systems of vectorizedadjoint_b200/examples/tape_systems.hpp through the reference's
+    #    AADC recording. Gradients only for the AUTONOMOUS variants: the reference's reverse sweep evaluates every stage at t_n
+    #    (detail/backpropagation.hpp:48,127), which is wrong for an explicitly time-dependent right-hand side; for those the
+    #    forward sweep (odeint handles t correctly) is pinned and the gradient is checked by finite differences in the tests.
+    rng = np.random.default_rng(20261018)
+    B = 16
+    pend_p = np.array([1.3, 0.15, 0.8]) * (1.0 + 0.2 * rng.uniform(-1, 1, (B, 3)))
+    pend_x0 = np.array([0.4, -0.2]) + 0.1 * rng.uniform(-1, 1, (B, 2))
+    sw_p = np.array([1.1, 0.4, 0.7]) * (1.0 + 0.2 * rng.uniform(-1, 1, (B, 3)))
+    sw_x0 = np.array([0.6, 0.3]) + 0.1 * rng.uniform(-1, 1, (B, 2))
+    pend_p[0], pend_x0[0], sw_p[0], sw_x0[0] = [1.3, 0.15, 0.8], [0.4, -0.2], [1.1, 0.4, 0.7], [0.6, 0.3]  # the examples' own inputs
+    seeds = rng.standard_normal((B, 2, 2))
+    arrays.update(tape_pendulum_params=pend_p, tape_pendulum_x0=pend_x0, tape_switched_params=sw_p, tape_switched_x0=sw_x0, tape_seeds=seeds)
+    for sysname, sid, sid_auto, pp, xx, tf in (("pendulum", oracle.SYS_PENDULUM, oracle.SYS_PENDULUM_AUTONOMOUS, pend_p, pend_x0, 2.0),
+                                               ("switched", oracle.SYS_SWITCHED, oracle.SYS_SWITCHED_AUTONOMOUS, sw_p, sw_x0, 3.0)):
+        for stname, st, tol, dt in (("rk4", oracle.RK_RK4, 0.0, 0.01), ("ck54_1e-8", oracle.RK_CK54, 1e-8, 0.01), ("rkf78_1e-8", oracle.RK_RKF78, 1e-8, 0.01)):
+            res = oracle.reference_forward_adjoint(sid_auto, 2, st, tol, tol, xx, pp, 0.0, tf, dt, objective=oracle.OBJ_SEED, seeds=seeds, nout=2)
+            k = f"tape_{sysname}_autonomous_{stname}"
+            arrays[k + "_steps"] = res["n_accept"]
+            arrays[k + "_x_final"] = res["x_final"]
+            arrays[k + "_lam"] = res["lam"]
+            arrays[k + "_mu"] = res["mu"]
+            res = oracle.reference_forward_adjoint(sid, 2, st, tol, tol, xx, pp, 0.0, tf, dt, objective=oracle.OBJ_SEED, seeds=seeds, nout=2)
+            k = f"tape_{sysname}_{stname}"
+            arrays[k + "_steps"] = res["n_accept"]
+            arrays[k + "_x_final"] = res["x_final"]  # forward sweep only (see above)
+    # 7. a recorded system wider than the per-lane register budget (16 species, 272 parameters): harvested Lotka-Volterra
+    N, B = 16, 8
+    p = oracle.synth_params(oracle.SYS_GLV, N, 4242, 0, B)
+    x0s = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    res = oracle.reference_forward_adjoint(oracle.SYS_HARVESTED_GLV, N, oracle.RK_CK54, 1e-8, 1e-8, x0s, p, 0.0, 10.0, 1e-3, objective=oracle.OBJ_SUM)
+    k = "tape_harvested_glv16_ck54_1e-8"
+    arrays[k + "_steps"] = res["n_accept"]
+    arrays[k + "_x_final"] = res["x_final"]
+    arrays[k + "_lam"] = res["lam"][:, 0]
+    arrays[k + "_mu"] = res["mu"][:, 0]
     np.savez_compressed(os.path.join(OUT, "reference_synth.npz"), **arrays)
     print("wrote", os.path.join(OUT, "reference_goldens.json"), "and reference_synth.npz")
 

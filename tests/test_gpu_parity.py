@@ -715,6 +715,24 @@ def test_glv256_onchip_and_ring_kernels_agree_with_streamed_kernel_and_oracle(va
 
 
 @pytest.mark.parametrize("kernel", ["k_glv_pair:2", "k_glv_pair:4", "k_glv_ring"])
+def test_glv256_against_the_reference_fixture(va, synth_goldens):
+    """BASELINE config 5 size: two parameter sets run through the UNMODIFIED reference + AADC (tests/golden/make_goldens.py
+    section 5), compared with the cluster-pair kernel directly (not via the C port)."""
+    N, B = 256, 2
+    g, k = synth_goldens, "glv_N256_ck54_1e-8"
+    p = oracle.synth_params(oracle.SYS_GLV, N, 1234, 0, B)
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+        r = e.forward_adjoint(oracle.synth_x0(oracle.SYS_GLV, N, p), p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+        assert e.info()["kernel_name"] == "k_glv_pair"
+    np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
+    assert_close(r["x_final"], g[k + "_x_final"], what="x(tf)")
+    assert_close(r["lam"][:, 0], g[k + "_lam"], what="lambda")
+    assert_close(r["mu"][:, 0, :N], g[k + "_mu_r"], what="mu, growth rates")
+    assert_close(r["mu"][:, 0, N::16], g[k + "_mu_A_every16"], what="mu, every 16th matrix entry")
+    np.testing.assert_allclose(r["mu"][:, 0].sum(axis=1), g[k + "_mu_sum"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("kernel", ["k_glv_pair:2", "k_glv_pair:4", "k_glv_ring"])
 def test_glv256_many_waves_summed_mode(va, monkeypatch, kernel):
     """More trajectories than resident CTAs / CTA pairs (each integrates several trajectories and keeps adding to its
     partial-sum row): the summed gradient equals the sum of the per-trajectory gradients, and a replicated parameter set

@@ -1,0 +1,113 @@
+"""GPU: the tape path (recordDriverRHSFunction -> va::Tape -> CUDA rhs/vjp -> NVRTC -> thread-per-trajectory kernels) against
+fixtures made by the REFERENCE ITSELF from the same functor source: vectorizedadjoint_b200/examples/tape_systems.hpp is recorded by
+AADC (idouble) through the reference's public API in oracle/ref_driver.cpp (tests/golden/make_goldens.py, section 6-7), and by
+this repo's tape here. Replaces the self-referential check of round 1 (adjoint vs finite differences of the same GPU forward).
+
+Gradients are compared for the AUTONOMOUS variants only: the reference's reverse sweep evaluates every stage at t_n
+(reference lib/include/detail/backpropagation.hpp:48,127), which is wrong for an explicitly time-dependent right-hand side; this
+engine uses t_n + c_m dt. For the time-dependent variants the forward sweep is pinned to the reference and the gradient to
+central finite differences.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "vectorizedadjoint_b200")
+RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def va():
+    import torch
+    assert torch.cuda.is_available()
+    import vectorizedadjoint_b200 as va
+    va.lib()
+    return va
+
+
+@pytest.fixture(scope="module")
+def emit(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("tape") / "tape_emit")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(PKG, "include"), "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(PKG, "examples"), os.path.join(ROOT, "tests", "tape_emit.cpp"), "-o", exe,
+                           "-L", PKG, "-lva_engine", f"-Wl,-rpath,{PKG}"])
+    cache = {}
+
+    def source(name):
+        if name not in cache:
+            cache[name] = subprocess.check_output([exe, name]).decode()
+        return cache[name]
+    return source
+
+
+def close(a, b, rtol=RTOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    scale = np.abs(b2).max(axis=1, keepdims=True)
+    scale[scale == 0] = 1.0
+    return float((np.abs(a2 - b2) / scale).max())
+
+
+STEPPERS = {"rk4": (1, False, 0.0), "ck54_1e-8": (2, True, 1e-8), "rkf78_1e-8": (4, True, 1e-8)}
+
+
+@pytest.mark.parametrize("system,tf", [("pendulum", 2.0), ("switched", 3.0)])
+@pytest.mark.parametrize("stname", list(STEPPERS))
+def test_recorded_systems_match_the_reference_aadc_recording(va, emit, synth_goldens, system, tf, stname):
+    g = synth_goldens
+    stepper, adaptive, tol = STEPPERS[stname]
+    p, x0, seeds = g[f"tape_{system}_params"], g[f"tape_{system}_x0"], g["tape_seeds"]
+    # autonomous variant: everything, two cost functions per trajectory (the reference's SIMD axis)
+    k = f"tape_{system}_autonomous_{stname}"
+    with va.Engine(va.SYS_TAPE, 2, stepper, adaptive, tol, tol, n_out=2, n_par=3, max_steps=512, tape_cuda_src=emit(system + "_autonomous")) as e:
+        assert e.info()["kernel_name"] == "jit"
+        r = e.forward_adjoint(x0, p, 0.0, tf, 0.01, objective=va.OBJ_SEED, seeds=seeds)
+    assert (r["status"] == 0).all()
+    np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
+    assert close(r["x_final"], g[k + "_x_final"]) <= 1e-12
+    assert close(r["lam"].reshape(len(p), -1), g[k + "_lam"].reshape(len(p), -1)) <= RTOL
+    assert close(r["mu"].reshape(len(p), -1), g[k + "_mu"].reshape(len(p), -1)) <= RTOL
+    # time-dependent variant: forward sweep vs the reference, gradient vs central finite differences of the forward map
+    k = f"tape_{system}_{stname}"
+    with va.Engine(va.SYS_TAPE, 2, stepper, adaptive, tol, tol, n_out=2, n_par=3, max_steps=512, tape_cuda_src=emit(system)) as e:
+        r = e.forward_adjoint(x0, p, 0.0, tf, 0.01, objective=va.OBJ_SEED, seeds=seeds)
+        np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
+        assert close(r["x_final"], g[k + "_x_final"]) <= 1e-12
+        if not adaptive:  # fixed step: the discrete map is smooth in p, finite differences are a valid check
+            h = 1e-6
+            for kpar in range(3):
+                pp, pm = p.copy(), p.copy()
+                pp[:, kpar] += h
+                pm[:, kpar] -= h
+                fp = e.forward_adjoint(x0, pp, 0.0, tf, 0.01, objective=va.OBJ_SEED, seeds=seeds)["x_final"]
+                fm = e.forward_adjoint(x0, pm, 0.0, tf, 0.01, objective=va.OBJ_SEED, seeds=seeds)["x_final"]
+                fd = np.einsum("boi,bi->bo", seeds, (fp - fm) / (2 * h))
+                assert np.abs(fd - r["mu"][:, :, kpar]).max() <= 2e-6 * np.abs(fd).max() + 1e-8
+
+
+def test_recorded_system_wider_than_the_register_budget(va, emit, synth_goldens):
+    """16 species, 272 parameters (more than a lane keeps in registers: they are read in place): the reference refuses
+    nothing by size (AadData::Record, reference lib/include/AadData.hpp:124-171), neither does the tape path."""
+    import oracle
+    g = synth_goldens
+    N, B = 16, 8
+    p = oracle.synth_params(oracle.SYS_GLV, N, 4242, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    k = "tape_harvested_glv16_ck54_1e-8"
+    with va.Engine(va.SYS_TAPE, N, va.RK_CK54, True, 1e-8, 1e-8, n_par=N * N + N, max_steps=256, tape_cuda_src=emit("harvested_glv16")) as e:
+        r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+        s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+        # more trajectories than one wave of lanes needs nothing special; a few hundred for the dynamic scheduler
+        pb = oracle.synth_params(oracle.SYS_GLV, N, 4242, 0, 700)
+        rb = e.forward_adjoint(oracle.synth_x0(oracle.SYS_GLV, N, pb), pb, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+    assert (r["status"] == 0).all() and (rb["status"] == 0).all()
+    np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
+    assert close(r["x_final"], g[k + "_x_final"]) <= 1e-12
+    assert close(r["lam"][:, 0], g[k + "_lam"]) <= RTOL
+    assert close(r["mu"][:, 0], g[k + "_mu"]) <= RTOL
+    assert close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True)) <= 1e-12
+    assert np.array_equal(rb["mu"][:B], r["mu"]) and np.array_equal(rb["x_final"][:B], r["x_final"])

@@ -38,6 +38,34 @@ int fail(int code, const std::string &msg) { return va_fail(code, msg); }
 
 namespace {
 
+// The persisting-L2 carve-out is DEVICE state: it shrinks the L2 every other kernel on the GPU sees (measured: the 16-species
+// kernel of a later engine ran 2.4x slower with an 83 MB carve-out left behind by a destroyed 64-species engine). Engines that
+// want it take a per-device reference; the last one to go restores the limit it found and drops the persisting lines.
+std::mutex g_persist_mutex;
+int g_persist_refs[64] = {0};
+size_t g_persist_prev[64] = {0};
+void persist_l2_acquire(va_engine *e, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_persist_mutex);
+    const int d = e->device & 63;
+    if (g_persist_refs[d]++ == 0) {
+        cudaDeviceGetLimit(&g_persist_prev[d], cudaLimitPersistingL2CacheSize);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+    }
+    e->holds_persist_l2 = true;
+}
+void persist_l2_release(va_engine *e)
+{
+    if (!e->holds_persist_l2) return;
+    std::lock_guard<std::mutex> lk(g_persist_mutex);
+    const int d = e->device & 63;
+    if (--g_persist_refs[d] == 0) {
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_persist_prev[d]);
+    }
+    e->holds_persist_l2 = false;
+}
+
 int ck_layout_of(const va_engine *e) { return e->desc.adaptive ? 1 : 0; } // see va_scalar_kernels.cuh: ck_store
 
 bool is_glv(const va_engine *e) { return e->family == FAM_GLV_WIDE || e->family == FAM_GLV_STREAM; }
@@ -378,8 +406,10 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
         break;
     case VA_SYS_TAPE:
         if (!desc->tape_cuda_src) return fail(VA_E_INVALID, "VA_SYS_TAPE needs tape_cuda_src (va::Tape::cuda_source(\"VaUserSys\"))");
-        if (desc->n_state > 16 || desc->n_par > 256)
-            return fail(VA_E_UNSUPPORTED, "recorded systems run on the thread-per-trajectory kernels: n_state <= 16, n_par <= 256");
+        // thread-per-trajectory kernels around the generated functor: state, stage slopes and stage adjoints are per-lane arrays
+        // (registers, spilling to local memory when wide), parameters beyond VA_REG_PARAMS are read in place. The bound below
+        // is the per-lane local-memory footprint ((2 s + 6) n doubles), not a limit of the tape.
+        if (desc->n_state > 64) return fail(VA_E_UNSUPPORTED, "recorded systems run on the thread-per-trajectory kernels: n_state <= 64");
         family = FAM_TAPE;
         break;
     default:
@@ -466,7 +496,7 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
             if (e->ring_flags & 2) {
                 int max_persist = 0;
                 if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device) == cudaSuccess && max_persist > 0)
-                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                    persist_l2_acquire(e, (size_t)max_persist);
             }
         }
     } else if (family == FAM_GLV_WIDE) {
@@ -497,7 +527,7 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
             // the kernel marks its checkpoint slabs evict_last: give that class the largest L2 share the device allows
             int max_persist = 0;
             if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device) == cudaSuccess && max_persist > 0)
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                persist_l2_acquire(e, (size_t)max_persist);
             if (getenv("VA_DEBUG")) fprintf(stderr, "va: persisting L2 limit %d bytes\n", max_persist);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
         } else {
@@ -529,6 +559,7 @@ void va_single_destroy(va_engine *e)
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     if (!e->comm_owned_by_head) va_comm_release(e);
+    persist_l2_release(e);
     DevBuf *bufs[] = {&e->slab, &e->partial, &e->xstore, &e->ck_t, &e->ck_x, &e->work_counter, &e->own_accept, &e->own_reject, &e->own_status, &e->mu_tmp,
                       &e->st_musum, &e->se_x0, &e->se_par, &e->se_xf, &e->se_lam, &e->se_mu, &e->se_acc, &e->se_rej, &e->se_sta};
     for (DevBuf *b : bufs) b->release();

@@ -103,6 +103,7 @@ struct va_engine {
     int comm_world = 0, comm_rank = 0;
     bool comm_owned_by_head = false;
     int64_t collectives = 0;
+    bool holds_persist_l2 = false;    // this engine holds a reference on its device's persisting-L2 carve-out
     bool mu_host_writer = true;       // host pipeline, VA_REDUCE_SUM: this engine copies the (all-reduced) sum to the caller's mu
 };
 

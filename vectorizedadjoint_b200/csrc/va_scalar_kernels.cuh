@@ -19,6 +19,15 @@
 #include "va_types.h"
 #include "va_pow.h"
 
+// Parameter placement. Up to VA_REG_PARAMS parameters a lane keeps its parameter set (and, in the reverse sweep, its gradient
+// accumulator) in registers. Wider recorded systems (a user-written Lotka-Volterra variant with 16 species has 272) read the
+// parameters where they lie -- params[b][k], through L1/L2 -- and accumulate dJ/dalpha directly in the caller's mu row, so the
+// thread-per-trajectory kernels have no parameter-count limit (reference: AadData::Record is size-agnostic,
+// lib/include/AadData.hpp:124-171).
+#ifndef VA_REG_PARAMS
+#define VA_REG_PARAMS 64
+#endif
+
 // Checkpoint store (the reference's StateStorage, lib/include/StateStorage.hpp:4-42) in HBM. Two layouts:
 //   ck_layout 0 (fixed step): t[n][b], x[n][i][b] -- trajectory index fastest. All lanes are at the same step n, so every
 //       access of a warp is one coalesced segment (harmonic oscillator: 57 % of HBM peak).
@@ -118,9 +127,11 @@ template <class Sys, int S, bool FSAL, bool ADAPTIVE>
 __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
 {
     constexpr int N = Sys::N, NPAR = Sys::NPAR;
+    constexpr bool PGLOBAL = NPAR > VA_REG_PARAMS;
     const VaTableau &tab = a.tab;
     const double tf = a.tf;
-    double x[N], p[NPAR], K[S][N], xnew[N], xerr[N];
+    double x[N], preg[PGLOBAL ? 1 : NPAR], K[S][N], xnew[N], xerr[N];
+    const double *p = preg;
     double t = 0.0, dt = 0.0;
     int64_t b = -1;
     int nck = 0, count = 0, rejects = 0, status = 0, trials = 0;
@@ -152,8 +163,11 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
             if (b >= a.B) break;
 #pragma unroll
             for (int i = 0; i < N; ++i) x[i] = a.x0[b * N + i];
+            if (PGLOBAL) p = a.params + b * NPAR;
+            else {
 #pragma unroll
-            for (int k = 0; k < NPAR; ++k) p[k] = a.params[b * NPAR + k];
+                for (int k = 0; k < NPAR; ++k) preg[k] = a.params[b * NPAR + k];
+            }
             t = a.ti; dt = a.dt0;
             nck = count = rejects = status = trials = 0;
             fresh = first_call = true;
@@ -225,9 +239,12 @@ template <class Sys, int S>
 __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
 {
     constexpr int N = Sys::N, NPAR = Sys::NPAR;
+    constexpr bool PGLOBAL = NPAR > VA_REG_PARAMS;
     const int64_t total = a.B * a.n_out;
     const VaTableau &tab = a.tab;
-    double p[NPAR], lam[N], mu[NPAR];
+    double preg[PGLOBAL ? 1 : NPAR], lam[N], mureg[PGLOBAL ? 1 : NPAR];
+    const double *p = preg;
+    double *mu = mureg;
     double K[S][N], W[S + 1][N], u[N], xm[N], gx[N];
     double t_next = 0.0;
     int64_t b = 0;
@@ -239,8 +256,10 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
             if (have) { // write back the finished work item
 #pragma unroll
                 for (int i = 0; i < N; ++i) lam_io[i] = lam[i];
+                if (!PGLOBAL) {
 #pragma unroll
-                for (int k = 0; k < NPAR; ++k) mu_out[k] = mu[k];
+                    for (int k = 0; k < NPAR; ++k) mu_out[k] = mureg[k];
+                }
                 have = false;
             }
             const int64_t w = (int64_t)atomicAdd(a.work_counter + 1, 1ULL);
@@ -250,8 +269,14 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
             b = w - (int64_t)o * a.B;
             lam_io = a.lambda + (b * a.n_out + o) * N;
             mu_out = a.mu + (b * a.n_out + o) * NPAR;
+            if (PGLOBAL) {
+                p = a.params + b * NPAR;
+                mu = mu_out; // the gradient accumulates in the caller's row
+                for (int k = 0; k < NPAR; ++k) mu_out[k] = 0.0;
+            } else {
 #pragma unroll
-            for (int k = 0; k < NPAR; ++k) { p[k] = a.params[b * NPAR + k]; mu[k] = 0.0; }
+                for (int k = 0; k < NPAR; ++k) { preg[k] = a.params[b * NPAR + k]; mureg[k] = 0.0; }
+            }
             if (a.status[b] & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS)) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) lam_io[i] = nan("");

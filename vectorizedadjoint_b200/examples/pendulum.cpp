@@ -8,19 +8,12 @@
 #include <iostream>
 
 #include "lib.hpp"
+#include "tape_systems.hpp"
 
 using namespace boost::numeric::odeint;
 using namespace vectorizedadjoint;
 
-struct DrivenPendulum {
-    double omega = 1.7; // not differentiated: a member, like k in the reference's harmonic oscillator
-    template <typename T>
-    void operator()(const std::vector<T> &x, std::vector<T> &dxdt, const std::vector<T> &p, const T t) const
-    {
-        dxdt[0] = x[1];
-        dxdt[1] = -p[0] * sin(x[0]) - p[1] * x[1] + p[2] * cos(omega * t) / (1.0 + x[0] * x[0]);
-    }
-};
+using tape_systems::DrivenPendulum; // tape_systems.hpp: the same source the reference's AADC records for the golden fixtures
 
 typedef runge_kutta4<std::vector<double>> fixed_type;
 typedef runge_kutta_dopri5<std::vector<double>> err_type;

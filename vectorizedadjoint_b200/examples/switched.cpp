@@ -8,23 +8,12 @@
 #include <iostream>
 
 #include "lib.hpp"
+#include "tape_systems.hpp"
 
 using namespace boost::numeric::odeint;
 using namespace vectorizedadjoint;
 
-struct Switched {
-    template <typename T>
-    void operator()(const std::vector<T> &x, std::vector<T> &dxdt, const std::vector<T> &p, const T t) const
-    {
-        using namespace std;
-        using va::iIf;
-        // restoring force that saturates (erf), a one-sided damper (iIf on the velocity), a soft floor (fmax) and a drive whose
-        // phase depends on the state (atan2)
-        const T damper = iIf(x[1] > 0.0, p[1] * x[1], 0.25 * p[1] * x[1]);
-        dxdt[0] = x[1];
-        dxdt[1] = -p[0] * erf(x[0]) - damper + p[2] * cos(t + atan2(x[1], 1.0 + x[0] * x[0])) + 0.1 * cbrt(1.0 + x[0] * x[0]) * fmax(x[0], -0.05);
-    }
-};
+using tape_systems::Switched; // tape_systems.hpp: the same source the reference's AADC records for the golden fixtures
 
 typedef runge_kutta4<std::vector<double>> fixed_type;
 

@@ -414,11 +414,14 @@ inline std::string Tape::cuda_source(const std::string &name) const
             o << ";\n";
         }
     };
-    o << "  __device__ static void rhs(const double *x, const double *p, double t, double *dx) {\n";
+    // a long tape is compiled once, as a real function, instead of being inlined into every stage of the stepper (the kernels
+    // call rhs / vjp s times each): compile time of a 40-species Lotka-Volterra variant drops from minutes to seconds
+    const char *inl = nodes.size() > 1500 ? "__noinline__ " : "";
+    o << "  " << inl << "__device__ static void rhs(const double *x, const double *p, double t, double *dx) {\n";
     forward();
     for (size_t i = 0; i < outputs.size(); ++i) o << "    dx[" << i << "] = " << v(outputs[i]) << ";\n";
     o << "  }\n";
-    o << "  __device__ static void vjp(const double *x, const double *p, double t, const double *w, double *gx, double *gp) {\n";
+    o << "  " << inl << "__device__ static void vjp(const double *x, const double *p, double t, const double *w, double *gx, double *gp) {\n";
     forward();
     for (size_t k = 0; k < nodes.size(); ++k) o << "    double " << d((int32_t)k) << " = 0.0;\n";
     for (size_t i = 0; i < outputs.size(); ++i) o << "    " << d(outputs[i]) << " += w[" << i << "];\n";
