@@ -714,7 +714,6 @@ def test_glv256_onchip_and_ring_kernels_agree_with_streamed_kernel_and_oracle(va
     assert_close(ha["mu"][:, 0], o["mu"], what="mu")
 
 
-@pytest.mark.parametrize("kernel", ["k_glv_pair:2", "k_glv_pair:4", "k_glv_ring"])
 def test_glv256_against_the_reference_fixture(va, synth_goldens):
     """BASELINE config 5 size: two parameter sets run through the UNMODIFIED reference + AADC (tests/golden/make_goldens.py
     section 5), compared with the cluster-pair kernel directly (not via the C port)."""
