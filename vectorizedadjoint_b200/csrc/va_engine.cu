@@ -70,7 +70,9 @@ int ck_layout_of(const va_engine *e) { return e->desc.adaptive ? 1 : 0; } // see
 
 bool is_glv(const va_engine *e) { return e->family == FAM_GLV_WIDE || e->family == FAM_GLV_STREAM; }
 
-int64_t per_traj_arena_bytes(const va_engine *e) { return (int64_t)(e->cap + 1) * (e->desc.n_state + 1) * 8; }
+// doubles per checkpoint record: layout 1 (adaptive) pads (t, x) to a multiple of four (VA_CK_REC in va_scalar_kernels.cuh)
+int ck_rec_doubles(const va_engine *e) { return e->desc.adaptive ? ((e->desc.n_state + 1 + 3) & ~3) : e->desc.n_state + 1; }
+int64_t per_traj_arena_bytes(const va_engine *e) { return (int64_t)(e->cap + 1) * ck_rec_doubles(e) * 8; }
 
 int ensure_workspace(va_engine *e, int64_t B)
 {
@@ -99,7 +101,7 @@ int ensure_workspace(va_engine *e, int64_t B)
     if (traj < B) traj = std::max<int64_t>(128, traj / 128 * 128); // whole CTAs per wave
     if (traj > e->arena_traj) {
         if (ck_layout_of(e) == 1) {
-            if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * (e->desc.n_state + 1) * 8)) return rc;
+            if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * ck_rec_doubles(e) * 8)) return rc;
         } else {
             if (int rc = e->ck_t.ensure((size_t)traj * (e->cap + 1) * 8)) return rc;
             if (int rc = e->ck_x.ensure((size_t)traj * (e->cap + 1) * e->desc.n_state * 8)) return rc;
@@ -764,8 +766,8 @@ int va_single_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double 
     VA_CUDA(cudaSetDevice(e->device));
     if (!is_glv(e)) {
         if (ck_layout_of(e) == 1) { // per-trajectory records {t, x}
-            const double *rec = e->ck_t.as<double>() + b * (int64_t)(e->cap + 1) * (n + 1);
-            const size_t pitch = (size_t)(n + 1) * 8;
+            const double *rec = e->ck_t.as<double>() + b * (int64_t)(e->cap + 1) * ck_rec_doubles(e);
+            const size_t pitch = (size_t)ck_rec_doubles(e) * 8;
             if (t) VA_CUDA(cudaMemcpy2D(t, 8, rec, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
             if (x) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, rec + 1, pitch, (size_t)n * 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         } else {

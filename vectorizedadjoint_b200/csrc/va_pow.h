@@ -71,15 +71,10 @@ VA_POW_HD double va_asdouble(uint64_t i)
 }
 
 // x: positive, finite, normal. y: finite with 2^-65 <= |y| < 2^63 and |y log x| < 512. Otherwise use the library pow.
-VA_POW_HD double va_pow_pos(double x, double y)
+// T, E: the two tables, wherever the caller keeps them (the kernels stage them in shared memory: the per-lane table gathers
+// were the top stall of the Van der Pol forward kernel when they went to global memory, profiles/r02/vdp_forward_ncu_full_before.txt).
+VA_POW_HD double va_pow_pos_t(double x, double y, const va_pow_logtab *T, const uint64_t *E)
 {
-#if defined(__CUDA_ARCH__)
-    const va_pow_logtab *T = va_pow_log_tab_d;
-    const uint64_t *E = va_pow_exp_tab_d;
-#else
-    const va_pow_logtab *T = va_pow_log_tab_h;
-    const uint64_t *E = va_pow_exp_tab_h;
-#endif
     const double A[7] = VA_POW_LOG_POLY;
     const double C[4] = VA_EXP_POLY; // C2..C5
     const double Ln2hi = VA_POW_LN2HI, Ln2lo = VA_POW_LN2LO;
@@ -166,7 +161,24 @@ VA_POW_HD double va_pow_pos(double x, double y)
 #endif
 }
 
+VA_POW_HD double va_pow_pos(double x, double y)
+{
+#if defined(__CUDA_ARCH__)
+    return va_pow_pos_t(x, y, va_pow_log_tab_d, va_pow_exp_tab_d);
+#else
+    return va_pow_pos_t(x, y, va_pow_log_tab_h, va_pow_exp_tab_h);
+#endif
+}
+
 // pow for the step-size controller: falls back to the library for arguments outside the fast path
+VA_POW_HD double va_pow_t(double x, double y, const va_pow_logtab *T, const uint64_t *E)
+{
+    const uint64_t ix = va_asuint64(x);
+    const uint32_t topx = (uint32_t)(ix >> 52);
+    const uint32_t topy = (uint32_t)(va_asuint64(y) >> 52) & 0x7ff;
+    if (topx - 0x001u >= 0x7ffu - 0x001u || topy - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
+    return va_pow_pos_t(x, y, T, E);
+}
 VA_POW_HD double va_pow(double x, double y)
 {
     const uint64_t ix = va_asuint64(x);

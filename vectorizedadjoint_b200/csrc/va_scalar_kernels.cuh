@@ -33,7 +33,11 @@
 //       access of a warp is one coalesced segment (harmonic oscillator: 57 % of HBM peak).
 //   ck_layout 1 (adaptive):   rec[b][n] = {t, x_0..x_{N-1}} -- one contiguous record stream per trajectory. With adaptive
 //       steps and dynamically scheduled lanes, neighbouring lanes are at unrelated (n, b); a lane then walks its own
-//       stream sequentially (24 B records share 32 B sectors / 128 B lines) instead of touching one sector per scalar.
+//       stream sequentially (one 32 B sector per record for two-state systems) instead of touching one sector per scalar.
+// Record stride of layout 1: (t, x_0..x_{N-1}) padded to a multiple of four doubles, so that a record never straddles a 32-byte
+// sector and, for two-state systems, is ONE 256-bit store / load (STG.256 / LDG.256, sm_100). With three separate 8-byte
+// stores per step the forward kernel stalled on its store queue (profiles/r02/vdp_forward_ncu_full_before.txt).
+#define VA_CK_REC(N) ((((N) + 1) + 3) & ~3)
 template <int N>
 __device__ __forceinline__ void ck_store(const VaScalarArgs &a, int64_t b, int n, double t, const double *x)
 {
@@ -42,28 +46,86 @@ __device__ __forceinline__ void ck_store(const VaScalarArgs &a, int64_t b, int n
 #pragma unroll
         for (int i = 0; i < N; ++i) a.ck_x[((int64_t)n * N + i) * a.arena_stride + b] = x[i];
     } else {
-        double *rec = a.ck_t + (b * (int64_t)(a.cap + 1) + n) * (N + 1);
-        rec[0] = t;
+        constexpr int REC = VA_CK_REC(N);
+        double *rec = a.ck_t + (b * (int64_t)(a.cap + 1) + n) * REC;
+        if (REC == 4) {
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "d"(t), "d"(x[0]), "d"(x[N > 1 ? 1 : 0]), "d"(x[N > 2 ? 2 : 0])
+                         : "memory");
+        } else {
+            rec[0] = t;
 #pragma unroll
-        for (int i = 0; i < N; ++i) rec[1 + i] = x[i];
+            for (int i = 0; i < N; ++i) rec[1 + i] = x[i];
+        }
     }
 }
 template <int N>
 __device__ __forceinline__ double ck_time(const VaScalarArgs &a, int64_t b, int n)
 {
-    return a.ck_layout == 0 ? a.ck_t[(int64_t)n * a.arena_stride + b] : a.ck_t[(b * (int64_t)(a.cap + 1) + n) * (N + 1)];
+    return a.ck_layout == 0 ? a.ck_t[(int64_t)n * a.arena_stride + b] : a.ck_t[(b * (int64_t)(a.cap + 1) + n) * VA_CK_REC(N)];
 }
+// time and state of checkpoint n in one access where the record allows it
 template <int N>
-__device__ __forceinline__ void ck_state(const VaScalarArgs &a, int64_t b, int n, double *x)
+__device__ __forceinline__ double ck_load(const VaScalarArgs &a, int64_t b, int n, double *x)
 {
     if (a.ck_layout == 0) {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = a.ck_x[((int64_t)n * N + i) * a.arena_stride + b];
-    } else {
-        const double *rec = a.ck_t + (b * (int64_t)(a.cap + 1) + n) * (N + 1) + 1;
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = rec[i];
+        return a.ck_t[(int64_t)n * a.arena_stride + b];
     }
+    constexpr int REC = VA_CK_REC(N);
+    const double *rec = a.ck_t + (b * (int64_t)(a.cap + 1) + n) * REC;
+    if (REC == 4) {
+        double r0, r1, r2, r3;
+        asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(rec) : "memory");
+        x[0] = r1;
+        if (N > 1) x[N > 1 ? 1 : 0] = r2;
+        if (N > 2) x[N > 2 ? 2 : 0] = r3;
+        return r0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = rec[1 + i];
+    return rec[0];
+}
+
+// Which tableau entries are non-zero, known at compile time. A kernel instantiation is one stepper -- (S, FSAL) identifies it:
+// 1 euler, 4 rk4, 6 cash_karp54, 7 + FSAL dopri5, 13 fehlberg78 -- so the zero weights of its tableau are dropped from the
+// unrolled sums by the compiler (same arithmetic on the non-zero terms: odeint sums exact zeros there). The VALUES still come
+// from the kernel argument (va_tableau.cpp). With run-time tests `if (a != 0.0)` a quarter of the forward kernel's instructions
+// were DSETP / FSEL pairs (profiles/r02/vdp_forward_ncu_full_after.txt).
+__device__ constexpr bool va_nz_a(int S, int m, int j)
+{
+    if (j >= m) return false;
+    if (S == 4) return j == m - 1;                            // rk4: sub-diagonal only
+    if (S == 7) return !(m == 6 && j == 1);                   // dopri5: the FSAL row is b, and b_1 = 0
+    if (S == 13) {                                            // fehlberg78
+        switch (m) {
+        case 1: case 2: return true;
+        case 3: return j != 1;
+        case 4: return j != 1;
+        case 5: return j == 0 || j >= 3;
+        case 6: return j == 0 || j >= 3;
+        case 7: return j == 0 || j >= 4;
+        case 8: return j == 0 || j >= 3;
+        case 9: return j == 0 || j >= 3;
+        case 10: return j == 0 || j >= 3;
+        case 11: return j == 0 || (j >= 5 && j <= 9);
+        case 12: return j == 0 || (j >= 3 && j != 10);
+        }
+    }
+    return true;                                              // euler (no entries), cash_karp54 (full lower triangle)
+}
+__device__ constexpr bool va_nz_b(int S, int j)
+{
+    if (S == 6) return j != 1 && j != 4;
+    if (S == 7) return j != 1 && j != 6;
+    if (S == 13) return (j >= 5 && j <= 9) || j >= 11;
+    return true;
+}
+__device__ constexpr bool va_nz_db(int S, int j)
+{
+    if (S == 6 || S == 7) return j != 1;
+    if (S == 13) return j == 0 || j >= 10;
+    return false;
 }
 
 // One explicit RK step in odeint's arithmetic order. K[0] = f(x,t) on entry.
@@ -81,8 +143,7 @@ __device__ __forceinline__ void rk_step(const VaTableau &tab, const double *x, c
             double acc = x[i];
 #pragma unroll
             for (int j = 0; j < m; ++j) {
-                const double a = tab.a[m * VA_MAX_STAGES + j];
-                if (a != 0.0) acc = acc + (a * dt) * K[j][i]; // a zero weight contributes an exact zero in odeint's sum
+                if (va_nz_a(S, m, j)) acc = acc + (tab.a[m * VA_MAX_STAGES + j] * dt) * K[j][i]; // zero weights add exact zeros in odeint's sum
             }
             xt[i] = acc;
         }
@@ -93,8 +154,7 @@ __device__ __forceinline__ void rk_step(const VaTableau &tab, const double *x, c
         double acc = x[i];
 #pragma unroll
         for (int j = 0; j < SE; ++j) {
-            const double b = tab.b[j];
-            if (b != 0.0) acc = acc + (b * dt) * K[j][i];
+            if (va_nz_b(S, j)) acc = acc + (tab.b[j] * dt) * K[j][i];
         }
         xnew[i] = acc;
     }
@@ -106,9 +166,8 @@ __device__ __forceinline__ void rk_step(const VaTableau &tab, const double *x, c
             bool first = true;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                const double d = tab.db[j];
-                if (d != 0.0) {
-                    const double term = (dt * d) * K[j][i];
+                if (va_nz_db(S, j)) {
+                    const double term = (dt * tab.db[j]) * K[j][i];
                     acc = first ? term : acc + term;
                     first = false;
                 }
@@ -136,6 +195,14 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
     int64_t b = -1;
     int nck = 0, count = 0, rejects = 0, status = 0, trials = 0;
     bool active = false, fresh = true, first_call = true;
+    // the controller's pow() tables (5 KB) staged in shared memory: every attempt gathers one entry of each per lane
+    __shared__ va_pow_logtab s_logtab[ADAPTIVE ? 128 : 1];
+    __shared__ uint64_t s_exptab[ADAPTIVE ? 256 : 1];
+    if (ADAPTIVE) {
+        for (int k = threadIdx.x; k < 128; k += blockDim.x) s_logtab[k] = va_pow_log_tab_d[k];
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_exptab[k] = va_pow_exp_tab_d[k];
+        __syncthreads();
+    }
 
     auto push = [&]() -> bool {
         if (nck > a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; return false; }
@@ -209,7 +276,7 @@ __device__ __forceinline__ void scalar_forward_body(const VaScalarArgs &a)
             if (reject || grow) {
                 const double base = reject ? err : fmax(tab.growth_floor, err); // growth_floor = pow(5.0, -stepper_order)
                 const double expo = reject ? -1.0 / ((double)tab.error_order - 1.0) : -1.0 / (double)tab.stepper_order;
-                const double pw = va_pow(base, expo);
+                const double pw = va_pow_t(base, expo, s_logtab, s_exptab);
                 factor = reject ? fmax(0.9 * pw, 0.2) : 9.0 / 10.0 * pw;
             }
             if (reject) {
@@ -240,6 +307,9 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
 {
     constexpr int N = Sys::N, NPAR = Sys::NPAR;
     constexpr bool PGLOBAL = NPAR > VA_REG_PARAMS;
+    // S counts the stages that carry weight in the adjoint: 6 is cash_karp54 or dopri5 without its FSAL stage -- both have a full
+    // lower triangle there, so the a-mask of "6 stages" is right for either (the b weights are taken at run time)
+    constexpr int SFULL = S;
     const int64_t total = a.B * a.n_out;
     const VaTableau &tab = a.tab;
     double preg[PGLOBAL ? 1 : NPAR], lam[N], mureg[PGLOBAL ? 1 : NPAR];
@@ -296,10 +366,9 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
             have = true;
             if (n < 0) continue;
         }
-        const double time = ck_time<N>(a, b, n);
+        const double time = ck_load<N>(a, b, n, u);
         const double dt = t_next - time; // StateStorage::GetDt: difference of stored times
         t_next = time;
-        ck_state<N>(a, b, n, u);
         // stage recompute, detail/backpropagation.hpp:37-52. The reference passes t_n to every stage (:48) and indexes
         // c(m) off by one in the VJP (:127); harmless there because its examples are autonomous. Here stage m is
         // evaluated at t_n + c_m dt, so recorded non-autonomous systems differentiate correctly.
@@ -309,8 +378,10 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
             for (int i = 0; i < N; ++i) xm[i] = u[i];
 #pragma unroll
             for (int j = 0; j < m; ++j)
+                if (va_nz_a(SFULL, m, j)) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[m * VA_MAX_STAGES + j] * K[j][i];
+                    for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[m * VA_MAX_STAGES + j] * K[j][i];
+                }
             Sys::rhs(xm, p, time + tab.c[m] * dt, K[m]);
         }
 #pragma unroll
@@ -325,14 +396,17 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
             for (int i = 0; i < N; ++i) xm[i] = u[i];
 #pragma unroll
             for (int k = 1; k < m; ++k)
+                if (va_nz_a(SFULL, m - 1, k - 1)) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * K[k - 1][i];
+                    for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * K[k - 1][i];
+                }
             Sys::vjp(xm, p, time + tab.c[m - 1] * dt, W[m], gx, mu);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 W[0][i] += gx[i];
 #pragma unroll
-                for (int k = 1; k < m; ++k) W[k][i] += gx[i] * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * dt;
+                for (int k = 1; k < m; ++k)
+                    if (va_nz_a(SFULL, m - 1, k - 1)) W[k][i] += gx[i] * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * dt;
             }
         }
 #pragma unroll
