@@ -302,7 +302,8 @@ def side_workload(args):
             "failed_trajectories": int((status != 0).sum()), "clocks": clk}
     if system == va.SYS_GLV:
         f_rhs, f_vjp = 2 * n * n + 2 * n, 4 * n * n + 3 * n
-        flops = (stages * T + (stages - 1) * R) * f_rhs + stages * T * f_vjp  # this rank's shard
+        recompute = eng.info()["ckpt_policy"] == va.CKPT_RECOMPUTE  # the stages are evaluated again in the reverse sweep (executed work)
+        flops = (stages * T + (stages - 1) * R + (stages * T if recompute else 0)) * f_rhs + stages * T * f_vjp  # this rank's shard
         peak = va.measure_fp64_peak(local)
         line["roofline"] = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                             "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "scope": "rank 0's shard on its GPU"}
@@ -494,12 +495,16 @@ def side_measure(va, torch, device, name, Btot, steps, warmup=2):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / steps
         kernel = eng.info()["kernel_name"]
+        recompute = eng.info()["ckpt_policy"] == va.CKPT_RECOMPUTE
     T, R = int(n_acc.sum(dtype=torch.int64)), int(n_rej.sum(dtype=torch.int64))
     res = {"value": Btot / (ms * 1e-3), "unit": "gradients/s", "batch": Btot, "ms_per_step": ms, "steps": steps, "kernel": kernel,
            "mean_accepted_steps": T / Btot, "failed_trajectories": int((status != 0).sum())}
     if system == va.SYS_GLV:
-        flops = (stages * T + (stages - 1) * R) * (2 * n * n + 2 * n) + stages * T * (4 * n * n + 3 * n)
-        res.update(bound="fp64", achieved_tflops=flops / (ms * 1e-3) / 1e12)
+        # executed algorithmic flops: forward (6T+5R) products, reverse 6T vector-Jacobian products, and -- under the recompute
+        # policy (the reference's) -- the 6T stage products evaluated again in the reverse sweep
+        flops = (stages * T + (stages - 1) * R + (stages * T if recompute else 0)) * (2 * n * n + 2 * n) + stages * T * (4 * n * n + 3 * n)
+        res.update(bound="fp64", achieved_tflops=flops / (ms * 1e-3) / 1e12, ckpt_policy="recompute" if recompute else "store_stages",
+                   useful_tflops_store_stages_formula=((stages * T + (stages - 1) * R) * (2 * n * n + 2 * n) + stages * T * (4 * n * n + 3 * n)) / (ms * 1e-3) / 1e12)
     else:
         byts = 2 * 8 * (n + 1) * (T + Btot) + Btot * 8 * (npar + 3 * n + npar)
         res.update(bound="hbm", achieved_gbs=byts / (ms * 1e-3) / 1e9)

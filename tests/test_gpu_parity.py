@@ -553,26 +553,28 @@ def test_glv_register_kernel_generations_agree(va, monkeypatch, N, B):
                                                             (5, 33, 2, True, 1e-5, 10.0, 1e-3), (16, 21, 1, False, 0.0, 0.3, 0.01),
                                                             (3, 5, 2, True, 1e-8, 3.0, 1e-3)])
 def test_glv_quad_kernel_agrees_with_first_generation_and_oracle(va, monkeypatch, N, B, stepper, adaptive, tol, tf, dt0):
-    """Up to 16 species run on va_glv_quad.cu (four lanes per trajectory, eight trajectories per warp in lock step, three
-    phases); VA_GLV_NO_QUAD selects the first-generation kernel (va_glv_wide.cu, a warp per trajectory). Independent
-    thread/data maps of the same algorithm: cross-check them and the oracle, with trajectories of different step counts
-    sharing a warp, idle quads, padded species counts, two seeds, the summed mode and ti == tf."""
+    """Up to 16 species run on va_glv_oct.cu by default (eight lanes per trajectory, A and Abar resident, recompute policy);
+    the store-stages policy selects va_glv_quad.cu (four lanes per trajectory, eight trajectories per warp in lock step, three
+    phases), VA_GLV_NO_QUAD the first-generation kernel (va_glv_wide.cu, a warp per trajectory). Three independent thread/data
+    maps (and two checkpoint policies) of the same algorithm: cross-check them and the oracle, with trajectories of different
+    step counts sharing a warp, idle lanes, padded species counts, two seeds, the summed mode and ti == tf."""
     p = oracle.synth_params(oracle.SYS_GLV, N, 606, 0, B)
     p[::3, :N] *= 3.0  # spread the growth rates so that neighbouring trajectories take different numbers of steps
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
     seeds = np.random.default_rng(3).standard_normal((B, 2, N))
     res = []
-    for quad in (True, False):
-        if not quad:
+    for kernel in ("k_glv_oct", "k_glv_quad", "k_glv_wide"):
+        policy = va.CKPT_AUTO if kernel == "k_glv_oct" else va.CKPT_STORE_STAGES
+        if kernel == "k_glv_wide":
             monkeypatch.setenv("VA_GLV_NO_QUAD", "1")
-        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, n_out=2) as e:
-            assert e.info()["kernel_name"] == ("k_glv_quad" if quad else "k_glv_wide")
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, n_out=2, ckpt_policy=policy) as e:
+            assert e.info()["kernel_name"] == kernel
             r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds)
             s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
             z = e.forward_adjoint(x0, p, 2.0, 2.0, dt0, objective=va.OBJ_SEED, seeds=seeds)  # ti == tf: no step at all
             e.forward(x0[:50], p[:50], 0.0, tf, dt0)
             t, x = e.checkpoints(min(B, 50) - 1)
-        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol) as e:
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, ckpt_policy=policy) as e:
             h = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_HALF_NORM2)
             hs = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_HALF_NORM2, reduce=va.REDUCE_SUM)
         assert (r["status"] == 0).all() and (z["n_accept"] == 0).all()
@@ -584,17 +586,22 @@ def test_glv_quad_kernel_agrees_with_first_generation_and_oracle(va, monkeypatch
         assert len(t) == r["n_accept"][min(B, 50) - 1] + 1 and t[0] == 0.0
         np.testing.assert_array_equal(x[0], x0[min(B, 50) - 1])
         res.append((r, h))
-    (a, ha), (b, hb) = res
-    np.testing.assert_array_equal(a["n_accept"], b["n_accept"])
-    assert_close(a["x_final"], b["x_final"], rtol=1e-12, what="x(tf)")
-    assert_close(a["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-10, what="lambda")
-    assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-10, what="mu")
+    (c, hc), (a, ha), (b, hb) = res
+    for other in (a, c):
+        np.testing.assert_array_equal(other["n_accept"], b["n_accept"])
+        assert_close(other["x_final"], b["x_final"], rtol=1e-12, what="x(tf)")
+        assert_close(other["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-10, what="lambda")
+        assert_close(other["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-10, what="mu")
     o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0, p, 0.0, tf, dt0, objective=oracle.OBJ_HALF_NORM2, threads=8)
     np.testing.assert_array_equal(ha["n_accept"], o["n_accept"])
     assert_close(ha["x_final"], o["x_final"], what="x(tf)")
     assert_close(ha["lam"][:, 0], o["lam"], what="lambda")
     assert_close(ha["mu"][:, 0], o["mu"], what="mu")
     assert_close(hb["mu"][:, 0], o["mu"], what="mu (first generation)")
+    np.testing.assert_array_equal(hc["n_accept"], o["n_accept"])
+    assert_close(hc["x_final"], o["x_final"], what="x(tf) (eight-lane kernel)")
+    assert_close(hc["lam"][:, 0], o["lam"], what="lambda (eight-lane kernel)")
+    assert_close(hc["mu"][:, 0], o["mu"], what="mu (eight-lane kernel)")
 
 
 def test_glv_quad_large_step_capacity_shrinks_the_grid(va):
@@ -604,7 +611,7 @@ def test_glv_quad_large_step_capacity_shrinks_the_grid(va):
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
     out = []
     for cap, frac in ((0, 0.0), (2000, 0.05)):  # 9472 slabs x 2001 blocks x 1600 B = 30 GB > 5 % of HBM -> fewer CTAs
-        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, max_steps=cap, workspace_fraction=frac) as e:
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, max_steps=cap, workspace_fraction=frac, ckpt_policy=va.CKPT_STORE_STAGES) as e:
             info = e.info()
             assert info["kernel_name"] == "k_glv_quad"
             r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
@@ -614,15 +621,17 @@ def test_glv_quad_large_step_capacity_shrinks_the_grid(va):
     np.testing.assert_array_equal(out[0]["x_final"], out[1]["x_final"])
 
 
-def test_glv16_several_trajectories_per_quad(va):
-    """More parameter sets than resident quads (148 x 64 on a B200): every quad integrates several trajectories and, in summed
-    mode, keeps adding to its partial-sum row; replicated parameter sets must give identical rows wherever they run."""
+@pytest.mark.parametrize("kernel", ["k_glv_oct", "k_glv_quad"])
+def test_glv16_several_trajectories_per_quad(va, kernel):
+    """More parameter sets than resident slots (148 x 32 / 148 x 64 on a B200): every slot integrates several trajectories and, in
+    summed mode, keeps adding to its partial-sum row; replicated parameter sets must give identical rows wherever they run."""
     N, B = 16, 30000
     base = oracle.synth_params(oracle.SYS_GLV, N, 99, 0, 7)
     p = base[np.arange(B) % 7]
     x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
-    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
-        assert e.info()["kernel_name"] == "k_glv_quad"
+    with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8,
+                   ckpt_policy=va.CKPT_AUTO if kernel == "k_glv_oct" else va.CKPT_STORE_STAGES) as e:
+        assert e.info()["kernel_name"] == kernel
         r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
         s = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
     assert (r["status"] == 0).all()

@@ -58,6 +58,14 @@ int va_glv_quad_slots_per_cta();
 int va_glv_quad_threads();
 cudaError_t va_glv_quad_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
+// second generation for up to 16 species (va_glv_oct.cu): eight lanes per trajectory, A and Abar both resident, recompute policy
+// (only (t_n, x_n) is stored; checkpoints [8-double header | x_n] per accepted step)
+bool va_glv_oct_supported(int n, int stepper, int adaptive);
+int va_glv_oct_block_doubles();
+int va_glv_oct_slots_per_cta();
+int va_glv_oct_threads();
+cudaError_t va_glv_oct_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
 // streamed-matrix GLV family (va_glv_stream.cu): any N, one 256-thread CTA per trajectory, same argument block
 bool va_glv_stream_supported(int n, int stepper, int adaptive);
 int va_glv_stream_block_doubles(int n, int stepper, int recompute);

@@ -199,7 +199,8 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
             a.reduce = native_sum ? VA_REDUCE_SUM : VA_REDUCE_NONE;
             a.mu = d.mu;
         }
-        if (e->family == FAM_GLV_WIDE && e->quad) VA_CUDA(va_glv_quad_forward_adjoint(a, st));
+        if (e->family == FAM_GLV_WIDE && e->oct) VA_CUDA(va_glv_oct_forward_adjoint(a, st));
+        else if (e->family == FAM_GLV_WIDE && e->quad) VA_CUDA(va_glv_quad_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
         else if (e->pairk) VA_CUDA(va_glv_pair_forward_adjoint(a, st));
@@ -399,8 +400,9 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
     case VA_SYS_GLV:
         if (desc->n_par != desc->n_state * desc->n_state + desc->n_state) return fail(VA_E_INVALID, "GLV: n_par must be N*N + N");
         if (va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_FORCE_STREAM") &&
-            desc->ckpt_policy != VA_CKPT_RECOMPUTE)
-            family = FAM_GLV_WIDE; // N <= 64: matrix in registers (store-stages policy only)
+            (desc->ckpt_policy != VA_CKPT_RECOMPUTE ||
+             (va_glv_oct_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_NO_OCT") && !getenv("VA_GLV_V1"))))
+            family = FAM_GLV_WIDE; // N <= 64: matrix in registers (store-stages policy; up to 16 species also recompute)
         else if (va_glv_stream_supported(desc->n_state, desc->stepper, desc->adaptive))
             family = FAM_GLV_STREAM; // any N: matrix streamed from L2/HBM
         else
@@ -506,8 +508,27 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
         e->t8 = va_glv_t8_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_V1");
         // up to 16 species: quad kernel (va_glv_quad.cu); VA_GLV_NO_QUAD keeps the first-generation kernel for cross-checks
         e->quad = va_glv_quad_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_NO_QUAD") && !getenv("VA_GLV_V1");
+        // up to 16 species, second generation (va_glv_oct.cu): the default unless the caller insists on the store-stages policy;
+        // VA_GLV_NO_OCT keeps the four-lane store-stages kernel for cross-checks
+        e->oct = va_glv_oct_supported(desc->n_state, desc->stepper, desc->adaptive) && desc->ckpt_policy != VA_CKPT_STORE_STAGES &&
+                 !getenv("VA_GLV_NO_OCT") && !getenv("VA_GLV_V1");
+        if (e->oct) e->quad = false;
         cudaError_t ce;
-        if (e->quad) {
+        if (e->oct) {
+            ce = cudaSuccess;
+            e->ctas_per_sm = 1;
+            e->grid = e->sm_count;
+            e->threads = va_glv_oct_threads();
+            e->tpc = va_glv_oct_slots_per_cta();
+            e->pair = 1;
+            e->glv_blk = va_glv_oct_block_doubles();
+            e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const double frac = desc->workspace_fraction > 0 ? desc->workspace_fraction : 0.5;
+                while (e->grid > 1 && (double)e->grid * e->tpc * e->slab_stride * 8.0 > frac * (double)free_b) e->grid = (e->grid + 1) / 2;
+            }
+        } else if (e->quad) {
             ce = cudaSuccess;
             e->ctas_per_sm = 1;
             e->grid = e->sm_count;
@@ -539,7 +560,7 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
             e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
         }
         if (ce != cudaSuccess) return bail(VA_E_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(ce));
-        e->desc.ckpt_policy = VA_CKPT_STORE_STAGES;
+        e->desc.ckpt_policy = e->oct ? VA_CKPT_RECOMPUTE : VA_CKPT_STORE_STAGES;
     } else {
         e->threads = 128;
         e->desc.ckpt_policy = VA_CKPT_RECOMPUTE;
@@ -596,7 +617,7 @@ static int single_get_info(va_engine *e, va_engine_info *info)
     info->chunk_trajectories = e->chunk_traj;
     info->kernel_launches = e->launches;
     info->last_kernel_ms = e->last_ms;
-    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->quad ? "k_glv_quad" : e->t8 ? "k_glv_t8" : "k_glv_wide")
+    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->oct ? "k_glv_oct" : e->quad ? "k_glv_quad" : e->t8 ? "k_glv_t8" : "k_glv_wide")
                      : e->pairk ? "k_glv_pair" : e->ring ? "k_glv_ring" : "k_glv_stream";
     std::snprintf(info->kernel_name, sizeof(info->kernel_name), "%s", kn);
     cudaDeviceProp prop;

@@ -66,7 +66,8 @@ struct va_engine {
     // wide family
     int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
     bool t8 = false;  // FAM_GLV_WIDE served by va_glv_t8.cu (33..64 species)
-    bool quad = false; // FAM_GLV_WIDE served by va_glv_quad.cu (up to 16 species)
+    bool quad = false; // FAM_GLV_WIDE served by va_glv_quad.cu (up to 16 species, store-stages policy)
+    bool oct = false;  // FAM_GLV_WIDE served by va_glv_oct.cu (up to 16 species, recompute policy: the default there)
     int glv_blk = 0;  // doubles per step block of the register-kernel slab
     bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
     int ring_flags = 0;
