@@ -68,6 +68,8 @@ def parse():
     ap.add_argument("--no-parity-sample", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=16384, help="parameter sets compared with the CPU oracle for flip_rate (N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic-probe", action="store_true", help="do not run the ncu DRAM-counter probe for roofline.traffic")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)  # child mode of the probe (runs under ncu)
     ap.add_argument("--cpu-sample", type=int, default=0, help="parameter sets per reference-arm step (0 = auto)")
     return ap.parse_args()
 
@@ -392,6 +394,55 @@ class GpmSampler:
             return {"error": repr(ex)[:120]}
 
 
+PROBE_SETS = 1 << 17  # parameter sets of the traffic probe launch (1/8 of the workload: same slots in flight, same per-set traffic)
+
+
+def traffic_probe_child():
+    """Child of live_traffic(): two launches of the headline kernel on PROBE_SETS device-resident parameter sets."""
+    import torch
+    import vectorizedadjoint_b200 as va
+    sh = DeviceShard(torch, va, 0, 0, PROBE_SETS, va.REDUCE_SUM)
+    with va.Engine(va.SYS_GLV, N_SPECIES, va.RK_CK54, True, TOL, TOL, device=0) as eng:
+        for _ in range(2):
+            a = sh.args(va, va.REDUCE_SUM)
+            Bn = a.pop("B")
+            eng.call("va_forward_adjoint_batch", Bn, a.pop("x0"), a.pop("params"), a.pop("ti"), a.pop("tf"), a.pop("dt0"), a.pop("x_final"),
+                     a.pop("lam"), a.pop("mu"), **a)
+        torch.cuda.synchronize()
+
+
+def live_traffic(device):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the headline kernel, measured now with ncu's DRAM counters in a
+    separate process (second launch of the probe, after a warm-up launch; nothing timed runs under the profiler). Returns
+    (bytes per parameter set, description) or (None, reason)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=(vis.split(",")[device] if vis else str(device)))  # the child's device 0 = this GPU
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:k_glv_t8", "--launch-skip", "1",
+           "--launch-count", "1", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-probe"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env).stdout
+    except Exception as ex:
+        return None, repr(ex)[:120]
+    import csv
+    import io
+    total = 0.0
+    found = 0
+    for row in csv.reader(io.StringIO(out)):
+        if len(row) > 3 and row[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            unit, val = row[-2].lower(), float(row[-1].replace(",", ""))
+            total += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1.0)
+            found += 1
+    if found != 2:
+        return None, "ncu gave no DRAM counters: " + out[-200:].replace("\n", " ")
+    return total / PROBE_SETS, (f"live: ncu dram__bytes_read.sum + dram__bytes_write.sum of one k_glv_t8 launch over {PROBE_SETS} parameter sets, taken in a "
+                                "separate process right after the timed run, scaled to this launch's parameter sets (per-set traffic does not depend "
+                                "on the batch once it exceeds the 592 resident slots)")
+
+
 def _committed_traffic():
     """DRAM bytes per full-size launch from the newest committed ncu --set full capture (fallback when GPM is unavailable)."""
     best = (None, None, None)
@@ -513,6 +564,9 @@ def side_measure(va, torch, device, name, Btot, steps, warmup=2):
 
 def main():
     args = parse()
+    if args.traffic_probe:
+        traffic_probe_child()
+        return
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -641,14 +695,23 @@ def main():
         ach = flops_exec / (kernel_ms * 1e-3) / 1e12
         alg_bytes = Bl * (8 * NPAR + 8 * N * 3) + (0 if red == va.REDUCE_SUM else Bl * 8 * NPAR)
         traffic, traffic_source = None, None
-        if gpm_vals and gpm_vals.get("dram_bw_util_pct") is not None:
+        if not args.no_traffic_probe and total == 1:
+            per_set, why = live_traffic(devices[0])
+            if per_set:
+                traffic, traffic_source = int(per_set * Bl), why
+            else:
+                traffic_source = why
+        if traffic is not None:
+            pass
+        elif gpm_vals and gpm_vals.get("dram_bw_util_pct") is not None:
             traffic = int(gpm_vals["dram_bw_util_pct"] / 100.0 * GpmSampler.DRAM_PEAK_BPS * kernel_ms * 1e-3)
             traffic_source = ("live: NVML GPM DRAM_BW_UTIL averaged over the timed region x 8.18 TB/s (3996 MHz x 2 x 8192 bit) x the launch "
                               "duration; cross-checked against the ncu --set full capture in profiles/")
         else:
             tb = _committed_traffic()
             if tb[0]:
-                traffic, traffic_source = int(tb[0] * Bl / tb[1]), f"committed ncu --set full capture profiles/{tb[2]} scaled to this shard (GPM unavailable)"
+                traffic, traffic_source = int(tb[0] * Bl / tb[1]), (f"committed ncu --set full capture profiles/{tb[2]} scaled to this shard "
+                                                                   f"(live probe: {traffic_source or 'not run at N > 1'})")
         line["roofline"] = {
             "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
             "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": alg_bytes, "gpm": gpm_vals,
