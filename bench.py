@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--reduce", default="sum", choices=["sum", "none"])
     ap.add_argument("--workload", default="glv64", choices=sorted(WORKLOADS), help="glv64 = the headline contract line")
     ap.add_argument("--species", type=int, default=0, help="with --workload glv256: any other species count (same tolerances; not a BASELINE config)")
-    ap.add_argument("--ckpt-policy", default="auto", choices=["auto", "recompute", "store"], help="side workloads: checkpoint policy of the engine")
+    ap.add_argument("--ckpt-policy", default="auto", choices=["auto", "recompute", "store", "sparse"], help="side workloads: checkpoint policy of the engine")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-side", action="store_true", help="skip the side block (the other BASELINE configs, N=1 only)")
     ap.add_argument("--no-check", action="store_true", help="N>1: skip the comparison with a one-GPU run of the whole batch")
@@ -260,7 +260,7 @@ def side_workload(args):
     mu = torch.empty((1, npar) if red == va.REDUCE_SUM else (B, 1, npar), **f64)
     n_acc, n_rej, status = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3))
     eng = va.Engine(system, n, stepper, adaptive, tol, tol, device=local, max_steps=max_steps,
-                    ckpt_policy={"auto": va.CKPT_AUTO, "recompute": va.CKPT_RECOMPUTE, "store": va.CKPT_STORE_STAGES}[args.ckpt_policy])
+                    ckpt_policy={"auto": va.CKPT_AUTO, "recompute": va.CKPT_RECOMPUTE, "store": va.CKPT_STORE_STAGES, "sparse": va.CKPT_SPARSE}[args.ckpt_policy])
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
 
@@ -298,13 +298,13 @@ def side_workload(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "batch_total": Btot, "reduce": args.reduce, "parallelism": f"batch sharded over {world} GPU(s)",
-                       "ckpt_policy": {va.CKPT_RECOMPUTE: "recompute", va.CKPT_STORE_STAGES: "store_stages"}.get(eng.info()["ckpt_policy"], "auto")},
+                       "ckpt_policy": {va.CKPT_RECOMPUTE: "recompute", va.CKPT_STORE_STAGES: "store_stages", va.CKPT_SPARSE: "sparse"}.get(eng.info()["ckpt_policy"], "auto")},
             "gpu_launches": info["kernel_launches"] - l0,
             "mean_accepted_steps": T / max(B, 1), "mean_rejected": R / max(B, 1), "max_accepted_steps": int(n_acc.max()) if B else 0,
             "failed_trajectories": int((status != 0).sum()), "clocks": clk}
     if system == va.SYS_GLV:
         f_rhs, f_vjp = 2 * n * n + 2 * n, 4 * n * n + 3 * n
-        recompute = eng.info()["ckpt_policy"] == va.CKPT_RECOMPUTE  # the stages are evaluated again in the reverse sweep (executed work)
+        recompute = eng.info()["ckpt_policy"] in (va.CKPT_RECOMPUTE, va.CKPT_SPARSE)  # the stages are evaluated again in the reverse sweep (executed work)
         flops = (stages * T + (stages - 1) * R + (stages * T if recompute else 0)) * f_rhs + stages * T * f_vjp  # this rank's shard
         peak = va.measure_fp64_peak(local)
         line["roofline"] = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
@@ -546,7 +546,7 @@ def side_measure(va, torch, device, name, Btot, steps, warmup=2):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / steps
         kernel = eng.info()["kernel_name"]
-        recompute = eng.info()["ckpt_policy"] == va.CKPT_RECOMPUTE
+        recompute = eng.info()["ckpt_policy"] in (va.CKPT_RECOMPUTE, va.CKPT_SPARSE)
     T, R = int(n_acc.sum(dtype=torch.int64)), int(n_rej.sum(dtype=torch.int64))
     res = {"value": Btot / (ms * 1e-3), "unit": "gradients/s", "batch": Btot, "ms_per_step": ms, "steps": steps, "kernel": kernel,
            "mean_accepted_steps": T / Btot, "failed_trajectories": int((status != 0).sum())}

@@ -75,7 +75,10 @@ enum va_mem { VA_MEM_HOST = 0, VA_MEM_DEVICE = 1 };
 enum va_ckpt_policy {
     VA_CKPT_AUTO = 0,
     VA_CKPT_RECOMPUTE = 1,   /* store accepted (t_n, x_n); recompute the stages in the reverse sweep (reference policy) */
-    VA_CKPT_STORE_STAGES = 2 /* additionally store the stage states/slopes of accepted steps; no recompute            */
+    VA_CKPT_STORE_STAGES = 2,/* additionally store the stage states/slopes of accepted steps; no recompute            */
+    VA_CKPT_SPARSE = 3       /* store t_n of every accepted step but x_n only of every L-th; the reverse sweep re-integrates
+                                each segment of L steps from its first state (checkpoint memory 8 + 8 N / L bytes per step).
+                                GLV 65..256 species (cluster kernel); elsewhere it means VA_CKPT_RECOMPUTE               */
 };
 /* per-trajectory status word (bit mask) */
 enum va_traj_status { VA_TRAJ_OK = 0, VA_TRAJ_CKPT_OVERFLOW = 1, VA_TRAJ_NO_PROGRESS = 2, VA_TRAJ_NONFINITE = 4 };

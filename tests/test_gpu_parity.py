@@ -517,6 +517,60 @@ def test_glv_auto_policy_long_horizon_uses_the_cluster_kernel(va):
     assert_close(r["lam"][:, 0], q["lam"][:, 0], rtol=1e-9, what="lambda")
 
 
+@pytest.mark.parametrize("seg", ["1", "5", "16", "64"])
+@pytest.mark.parametrize("N,tol,tf", [(256, 1e-8, 10.0), (100, 1e-12, 300.0)])
+def test_glv_sparse_checkpoints_on_the_cluster_kernel(va, monkeypatch, seg, N, tol, tf):
+    """VA_CKPT_SPARSE ('checkpoint scheduling beyond store-all'; the reference stores every accepted state,
+    lib/include/StateStorage.hpp:7-8): t_n of every accepted step, x_n of every L-th only; each segment is re-integrated from its
+    first state. Against the store-stages policy and the oracle, for segment lengths 1 (= dense), 5, 16 and longer than the
+    trajectory; a short horizon (~21 steps) and a long one (~150 steps); two seeds and the summed mode."""
+    B = 3
+    p = oracle.synth_params(oracle.SYS_GLV, N, 515, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(5).standard_normal((B, 2, N))
+    monkeypatch.setenv("VA_PAIR_SEG", seg)
+    res = {}
+    for pol in (va.CKPT_SPARSE, va.CKPT_STORE_STAGES):
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, tol, tol, n_out=2, max_steps=512, ckpt_policy=pol) as e:
+            info = e.info()
+            assert info["kernel_name"] == "k_glv_pair" and info["ckpt_policy"] == pol
+            r = e.forward_adjoint(x0, p, 0.0, tf, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
+            s = e.forward_adjoint(x0, p, 0.0, tf, 1e-3, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+            f = e.forward(x0, p, 0.0, tf, 1e-3)
+            if pol == va.CKPT_SPARSE:
+                with pytest.raises(va.EngineError, match="every L-th"):
+                    e.checkpoints(1)  # the intermediate states are not there: the call says so instead of returning something else
+            ws = info["workspace_bytes"] or e.info()["workspace_bytes"]
+        assert (r["status"] == 0).all()
+        assert_close(s["mu"], r["mu"].sum(axis=0), rtol=1e-11, what="mu sum")
+        res[pol] = (r, f, ws)
+    (a, fa, wa), (b, fb, wb) = res[va.CKPT_SPARSE], res[va.CKPT_STORE_STAGES]
+    np.testing.assert_array_equal(a["n_accept"], b["n_accept"])
+    np.testing.assert_array_equal(a["x_final"], b["x_final"])
+    assert_close(a["lam"].reshape(B * 2, -1), b["lam"].reshape(B * 2, -1), rtol=1e-9, what="lambda")
+    assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-9, what="mu")
+    assert wa < wb / 4  # what it is for: checkpoint memory (segment slab + times + every L-th state against 513 stage blocks per CTA)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, oracle.RK_CK54, True, tol, tol, x0, p, 0.0, tf, 1e-3, objective=oracle.OBJ_SEED,
+                               seeds=seeds[:, 0], threads=8)
+    np.testing.assert_array_equal(a["n_accept"], o["n_accept"])
+    assert_close(a["lam"][:, 0], o["lam"], what="lambda vs oracle")
+    assert_close(a["mu"][:, 0], o["mu"], what="mu vs oracle")
+
+
+def test_glv_auto_policy_picks_sparse_checkpoints_for_very_long_horizons(va):
+    """VA_CKPT_AUTO: stage blocks too large -> recompute; one state per step still too large -> sparse."""
+    with va.Engine(va.SYS_GLV, 256, va.RK_CK54, True, 1e-8, 1e-8, max_steps=2_000_000) as e:
+        info = e.info()  # 148 x 2e6 x 2.1 KB = 625 GB of states: more than the GPU has
+        assert info["kernel_name"] == "k_glv_pair" and info["ckpt_policy"] == va.CKPT_SPARSE
+        p = oracle.synth_params(oracle.SYS_GLV, 256, 3, 0, 2)
+        x0 = oracle.synth_x0(oracle.SYS_GLV, 256, p)
+        r = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+        assert e.info()["workspace_bytes"] < 60e9
+    o = oracle.forward_adjoint(oracle.SYS_GLV, 256, oracle.RK_CK54, True, 1e-8, 1e-8, x0, p, 0.0, 10.0, 1e-3, objective=oracle.OBJ_SUM, threads=2)
+    np.testing.assert_array_equal(r["n_accept"], o["n_accept"])
+    assert_close(r["mu"][:, 0], o["mu"], what="mu")
+
+
 @pytest.mark.parametrize("N,B", [(64, 5), (50, 3), (64, 1)])
 def test_glv_register_kernel_generations_agree(va, monkeypatch, N, B):
     """33..64 species run on va_glv_t8.cu (64 threads per trajectory, 8x8 tiles, three phases); VA_GLV_V1 selects the

@@ -31,7 +31,7 @@ RK_EULER, RK_RK4, RK_CK54, RK_DOPRI5, RK_RKF78 = 0, 1, 2, 3, 4
 OBJ_SEED, OBJ_SUM, OBJ_HALF_NORM2 = 0, 1, 2
 REDUCE_NONE, REDUCE_SUM = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-CKPT_AUTO, CKPT_RECOMPUTE, CKPT_STORE_STAGES = 0, 1, 2
+CKPT_AUTO, CKPT_RECOMPUTE, CKPT_STORE_STAGES, CKPT_SPARSE = 0, 1, 2, 3
 TRAJ_OK, TRAJ_CKPT_OVERFLOW, TRAJ_NO_PROGRESS, TRAJ_NONFINITE = 0, 1, 2, 4
 
 HOST_DEFAULT, HOST_WRITE_COMBINED, HOST_NUMA_LOCAL = 0, 1, 2

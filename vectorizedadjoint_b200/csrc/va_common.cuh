@@ -36,6 +36,7 @@ struct VaGlvWideArgs {
     double *xstore;
     int64_t xstore_stride;
     int seg_len;
+    int sparse;           // cluster kernel, recompute policy: keep t_n of every step but x_n only of every seg_len-th (VA_CKPT_SPARSE)
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);

@@ -186,8 +186,9 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
             a.xstore = e->xstore.as<double>();
             a.xstore_stride = e->xstore_stride;
             a.seg_len = e->pair_seg_len;
+            a.sparse = e->pair_sparse ? 1 : 0;
         }
-        a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE;
+        a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE || e->desc.ckpt_policy == VA_CKPT_SPARSE;
         a.blk_doubles = e->glv_blk;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
         if (sum && !native_sum && !d.forward_only) {
@@ -400,7 +401,7 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
     case VA_SYS_GLV:
         if (desc->n_par != desc->n_state * desc->n_state + desc->n_state) return fail(VA_E_INVALID, "GLV: n_par must be N*N + N");
         if (va_glv_wide_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_FORCE_STREAM") &&
-            (desc->ckpt_policy != VA_CKPT_RECOMPUTE ||
+            ((desc->ckpt_policy != VA_CKPT_RECOMPUTE && desc->ckpt_policy != VA_CKPT_SPARSE) ||
              (va_glv_oct_supported(desc->n_state, desc->stepper, desc->adaptive) && !getenv("VA_GLV_NO_OCT") && !getenv("VA_GLV_V1"))))
             family = FAM_GLV_WIDE; // N <= 64: matrix in registers (store-stages policy; up to 16 species also recompute)
         else if (va_glv_stream_supported(desc->n_state, desc->stepper, desc->adaptive))
@@ -463,7 +464,12 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
             const double need = e->pairk ? (double)e->sm_count * (e->cap + 1) * va_glv_pair_block_doubles(desc->stepper) * 8.0
                                          : (double)e->grid * (e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, 0) * 8.0;
             policy = need > frac * (double)free_b ? VA_CKPT_RECOMPUTE : VA_CKPT_STORE_STAGES;
+            // ... and when even one state per accepted step is too much (2.1 KB x capacity x 148 CTAs), every L-th state only
+            if (policy == VA_CKPT_RECOMPUTE && e->pairk &&
+                (double)e->sm_count * (e->cap + 1) * (8 + 256) * 8.0 > frac * (double)free_b)
+                policy = VA_CKPT_SPARSE;
         }
+        if (policy == VA_CKPT_SPARSE && !e->pairk) policy = VA_CKPT_RECOMPUTE; // only the cluster kernel thins its state store
         e->desc.ckpt_policy = policy;
         e->slab_stride = (int64_t)(e->cap + 1) * va_glv_stream_block_doubles(desc->n_state, desc->stepper, policy == VA_CKPT_RECOMPUTE);
         e->ring = !e->pairk && policy == VA_CKPT_STORE_STAGES && va_glv_ring_supported(desc->n_state, desc->stepper, desc->adaptive) &&
@@ -479,7 +485,8 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
             if (getenv("VA_DEBUG")) fprintf(stderr, "va: k_glv_pair: %d clusters of %d CTAs\n", e->grid / e->pair_cl, e->pair_cl);
             e->glv_blk = va_glv_pair_block_doubles(desc->stepper);
             e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
-            e->pair_seg = policy == VA_CKPT_RECOMPUTE;
+            e->pair_seg = policy == VA_CKPT_RECOMPUTE || policy == VA_CKPT_SPARSE;
+            e->pair_sparse = policy == VA_CKPT_SPARSE;
             if (e->pair_seg) {
                 // recompute policy: (t_n, x_n) of every accepted step in a per-CTA state store, stage blocks only for one segment
                 // (16 steps x 36.9 KB x 148 CTAs = 87 MB: L2-resident); VA_PAIR_SEG overrides the segment length
@@ -487,6 +494,8 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
                 e->pair_seg_len = sl < 1 ? 1 : sl;
                 e->slab_stride = (int64_t)(e->pair_seg_len + 1) * e->glv_blk;
                 e->xstore_stride = (int64_t)(e->cap + 1) * (8 + 256);
+                if (e->pair_sparse) // [t_0 .. t_cap+1 | pad | one state per segment]  (va_glv_pair.cu)
+                    e->xstore_stride = ((int64_t)e->cap + 2 + 7) / 8 * 8 + ((int64_t)e->cap / e->pair_seg_len + 1) * 256;
             }
         }
         if (e->ring) {
@@ -800,6 +809,14 @@ int va_single_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double 
         // slab of CTA b: one block per accepted step, header[0] = t_n, then the stage states; stage 0 is x_n. Block T
         // carries the final time only; x_T is x(tf).
         // slab 0 of the slot (cluster-pair kernel: CTA 2 * slot of the pair)
+        if (e->pair_sparse) {
+            // sparse store: every time is there, the states only at segment starts
+            const double *tb = e->xstore.as<double>() + slot * e->pair_cl * e->xstore_stride;
+            if (t) VA_CUDA(cudaMemcpy(t, tb, ((size_t)T + 1) * 8, cudaMemcpyDeviceToHost));
+            if (x) return fail(VA_E_UNSUPPORTED, "VA_CKPT_SPARSE keeps the state of every L-th accepted step only: request the times (x = NULL), "
+                                                "or use VA_CKPT_RECOMPUTE / VA_CKPT_STORE_STAGES when Driver::GetState is needed");
+            return VA_OK;
+        }
         const double *base = e->pair_seg ? e->xstore.as<double>() + slot * e->pair_cl * e->xstore_stride
                                          : e->slab.as<double>() + slot * (e->pairk ? e->pair_cl : e->pair) * e->slab_stride;
         const size_t pitch = e->pair_seg ? (size_t)(8 + 256) * 8 : (size_t)(e->family == FAM_GLV_WIDE || e->ring || e->pairk ? e->glv_blk

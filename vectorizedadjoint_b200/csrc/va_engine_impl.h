@@ -75,6 +75,7 @@ struct va_engine {
     int pair_cl = 2;
     bool pair_seg = false; // ... under the recompute policy: per-CTA state store + segment re-integration
     int pair_seg_len = 16;
+    bool pair_sparse = false; // ... with the sparse state store (VA_CKPT_SPARSE): t_n of every step, x_n of every pair_seg_len-th
     int64_t xstore_stride = 0;
     DevBuf xstore;
     int64_t slab_stride = 0;

@@ -353,6 +353,14 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
     double *const slab = a.slab + (int64_t)blockIdx.x * a.slab_stride;
     constexpr int XB = 8 + N; // state-store entry: [8-double header (t_n) | x_n]
     double *const xstore = SEG ? a.xstore + (int64_t)blockIdx.x * a.xstore_stride : nullptr;
+    // SPARSE checkpoints (a.sparse, SURVEY section 8 f3: "checkpoint scheduling beyond store-all"): the store keeps t_n of every
+    // accepted step but x_n only of the first step of each segment (every seg_len-th step); the segment re-integration below
+    // then carries the state from step to step itself. 8 B + 8 N / seg_len B per step instead of 8 (N + 8) B.
+    //   layout: [t_0 .. t_cap+1 | pad to 8 | x of step 0 | x of step seg_len | ...]
+    const bool sparse = SEG && a.sparse;
+    const int64_t xs_states = ((int64_t)a.cap + 2 + 7) / 8 * 8;
+    auto ck_time = [&](int nn) -> double * { return sparse ? xstore + nn : xstore + (int64_t)nn * XB; };
+    auto ck_state = [&](int nn) -> double * { return sparse ? xstore + xs_states + (int64_t)(nn / a.seg_len) * N : xstore + (int64_t)nn * XB + 8; };
     double creg[CR];
     bool row_init = false; // summed mode: this pair's partial-sum row has been written
 
@@ -401,9 +409,8 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             if (fresh) {
                 if (nck >= a.cap) { status |= VA_TRAJ_CKPT_OVERFLOW; break; }
                 if (SEG) {
-                    double *xb = xstore + (int64_t)nck * XB;
-                    xb[8 + tid] = x;
-                    if (tid == 0) xb[0] = t;
+                    if (!sparse || nck % a.seg_len == 0) ck_state(nck)[tid] = x;
+                    if (tid == 0) *ck_time(nck) = t;
                 } else {
                     blk[OFF_X + tid] = x;
                     blk[OFF_G + tid] = g0;
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
         }
         const int T = nck;
         if (tid == 0) {
-            if (SEG) xstore[(int64_t)T * XB] = t; // entry T carries the final time
+            if (SEG) *ck_time(T) = t; // entry T carries the final time
             else slab[(int64_t)T * BLK] = t;
         }
         if (!isfinite(x)) status |= VA_TRAJ_NONFINITE;
@@ -532,7 +539,9 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             int s1 = T;
             bool first_seg = true;
             do {
-            const int s0 = SEG ? (s1 > a.seg_len ? s1 - a.seg_len : 0) : 0;
+            // segment boundaries are multiples of seg_len counted from step 0 (the newest segment may be shorter), so that every
+            // segment starts on a step whose state the sparse store holds
+            const int s0 = SEG && s1 > 0 ? (s1 - 1) / a.seg_len * a.seg_len : 0; // s1 == 0: a trajectory without steps (ti == tf)
             const int Tseg = s1 - s0;
             // The register rows are reloaded at the top of EVERY segment (and seed), although they never change: an unconditional
             // reload ends their live range before phase 3, whose 128 accumulator registers cannot coexist with them (a conditional or
@@ -540,10 +549,11 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
             load_rows();
             if (SEG) {
                 // ---- re-integration of the segment from the stored states ----
+                double xcarry = 0.0; // sparse store: x_{nn} as re-integrated from the segment's first state
 #pragma unroll 1
                 for (int nn = s0; nn < s1; ++nn) {
-                    const double *xb = xstore + (int64_t)nn * XB;
-                    const double xn = xb[8 + tid], tn = xb[0], tn1 = xb[XB];
+                    const double tn = *ck_time(nn), tn1 = *ck_time(nn + 1);
+                    const double xn = (!sparse || nn == s0) ? ck_state(nn)[tid] : xcarry;
                     const double dts = tn1 - tn;
                     double *blk = slab + (int64_t)(nn - s0) * BLK;
                     if (tid == 0) blk[0] = tn;
@@ -561,6 +571,13 @@ __global__ void __launch_bounds__(NT, 1) k_glv_pair(const __grid_constant__ VaGl
                         const double gm = product_rows(P, rr, creg, tid);
                         Kr[m] = xm * gm;
                         blk[OFF_G + m * N + tid] = gm;
+                    }
+                    if (sparse) { // x_{nn+1} = x_nn + dt sum_j b_j K_j, the forward sweep's own update
+                        double acc = 0.0;
+#pragma unroll
+                        for (int j = 0; j < SADJ; ++j)
+                            if (Tab::b(j) != 0.0) acc = fma(Tab::b(j), Kr[j], acc);
+                        xcarry = fma(dts, acc, xn);
                     }
                 }
                 __syncthreads();
