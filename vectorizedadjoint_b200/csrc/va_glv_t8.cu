@@ -46,6 +46,9 @@
 #ifndef VA_T8_NB
 #define VA_T8_NB 3 // step-block buffers per CTA
 #endif
+#ifndef VA_T8_MAP
+#define VA_T8_MAP 0 // warp -> trajectory map inside a CTA (see the kernel)
+#endif
 
 namespace {
 
@@ -126,8 +129,15 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     // that ptxas cannot move them: 4.82 M, 4.60 M and 4.53 M gradients/s against 5.7 M without. ncu shows bursts stretched
     // from ~155 to ~280 cycles by the neighbour, but serialising them costs more than the overlap.)
     const int wc = threadIdx.x >> 5;
+#if VA_T8_MAP == 1
+    // experiment: every warp of a trajectory shares its sub-partition with a DIFFERENT other trajectory
+    // (warps 0,1 -> slot 0; 2,3 -> slot 1; 4,6 -> slot 2; 5,7 -> slot 3)
+    const int slot = SLOTS == 1 ? 0 : (wc < 4 ? (wc >> 1) : 2 + (wc & 1));
+    const int warp = wc < 4 ? (wc & 1) : ((wc >> 1) & 1); // warp inside the trajectory
+#else
     const int slot = SLOTS == 1 ? 0 : ((wc >> 2) << 1) | ((wc >> 1) & 1);
     const int warp = wc & 1;                       // warp inside the trajectory
+#endif
     const int tid = warp * 32 + (threadIdx.x & 31); // thread inside the trajectory
     const int g = tid & (RT - 1); // lane inside the reduction group (RT lanes)
     const int hi = tid / RT;      // reduction group
