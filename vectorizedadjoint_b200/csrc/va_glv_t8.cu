@@ -44,10 +44,13 @@
 #define VA_T8_NC 1 // independent accumulator chains per tile row in a product (column pairs are dealt round-robin)
 #endif
 #ifndef VA_T8_NB
-#define VA_T8_NB 3 // step-block buffers per CTA
+#define VA_T8_NB 4 // step-block buffers per slot (2 / 3 / 4: 5.92 / 5.91 / 5.94 M gradients/s)
 #endif
 #ifndef VA_T8_MAP
 #define VA_T8_MAP 0 // warp -> trajectory map inside a CTA (see the kernel)
+#endif
+#ifndef VA_T8_P3
+#define VA_T8_P3 0 // phase 3 (Abar += v x^T): 0 = DFMA on 8x8 register tiles, 1 = FP64 tensor instructions (DMMA m8n8k4), see the kernel
 #endif
 
 namespace {
@@ -59,13 +62,28 @@ constexpr int NT = NTT * SLOTS; // threads per CTA
 constexpr int MINB = SLOTS == 1 ? VA_T8_MINB : 1;
 
 constexpr int HDR = 8;  // doubles in a step-block header (hdr[0] = t_n)
-constexpr int NB = VA_T8_NB;
+constexpr int NB = VA_T8_P3 ? 4 : VA_T8_NB;
+// DMMA variant of phase 3: a step's 2 x SADJ vectors sit in shared memory with a stride of 68 doubles (544 B = 32 B more than a
+// multiple of 128), so that the fragment loads -- lane l reads element (l >> 2) of vector (l & 3): four vectors, 32 bytes each
+// per half-warp -- touch every bank once; with the natural stride of 512 B they were 4-way bank conflicts
+constexpr int VS3 = 68;
 constexpr int RT = VA_T8_RT; // tile rows per thread = lanes per reduction group
 constexpr int CT = 64 / RT; // tile columns per thread
 constexpr int NC = VA_T8_NC;
 static_assert((RT == 8 || RT == 4 || RT == 2) && (NC == 1 || NC == 2 || NC == 4), "tile geometry");
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// doubles per shared-memory step buffer: a step block, or (DMMA variant of phase 3) its 2 x SADJ vectors at the padded stride
+// (+ 8: consecutive buffers are 64 B off the 128 B grid, so that a fragment group that spans two buffers stays conflict-free)
+__host__ __device__ constexpr int buf_doubles(int blk, int sadj) { return VA_T8_P3 && 2 * sadj * VS3 + 8 > blk ? 2 * sadj * VS3 + 8 : blk; }
+#if VA_T8_P3
+// D(8x8) += A(8x4) B(4x8) in FP64 on the tensor path: lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2], D[l >> 2][2 (l & 3) + {0, 1}]
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
 
 // mbarrier + TMA bulk copy + L2 eviction-policy helpers: va_tma.cuh (one copy for all kernels).
 // L2 residency control. The slabs (592 x ~130 KB of step blocks in flight per GPU) are written, read twice and then
@@ -152,7 +170,8 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     const bool vsep = voff != HDR + SADJ * NP;               // v has its own section (several seeds per trajectory)
     const int64_t gslot = (int64_t)blockIdx.x * SLOTS + slot; // global slot: owns one slab and one partial-sum row
     double *const slab = a.slab + gslot * a.slab_stride;
-    double *const xg = xg_all + (size_t)slot * NB * blk;
+    const int bstr = buf_doubles(blk, SADJ); // doubles per shared-memory step buffer
+    double *const xg = xg_all + (size_t)slot * NB * bstr;
     double(*xs)[NP] = xs_all[slot];
     double *red = red_all[slot];
     uint64_t *mbar = mbar_all[slot];
@@ -191,6 +210,17 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     double *const part = a.partial + gslot * npar;
     if (a.reduce == VA_REDUCE_SUM && a.n_out > 0) {
         if (own < n) part[own] = 0.0;
+#if VA_T8_P3
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J < 8; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = 32 * warp + 8 * I + ((tid & 31) >> 2), col = 8 * J + 2 * (tid & 3) + e;
+                    if (row < n && col < n) part[n + row * n + col] = 0.0;
+                }
+#else
 #pragma unroll
         for (int k = 0; k < 8; ++k)
 #pragma unroll
@@ -198,6 +228,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 const int row = FH(k), col = FG8(c);
                 if (row < n && col < n) part[n + row * n + col] = 0.0;
             }
+#endif
     }
     __syncthreads();
 
@@ -456,7 +487,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 if (it < T) {
                     const int bi = it % NB;
                     mbar_expect_tx(&mbar[bi], xg_bytes);
-                    bulk_g2s(xg + bi * blk, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi], keep);
+                    bulk_g2s(xg + bi * bstr, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi], keep);
                 }
             };
             slot_sync(); // every thread is past its reads of the buffers (previous seed / trajectory)
@@ -467,7 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 const int step = T - 1 - it, bi = it % NB;
                 mbar_wait(&mbar[bi], (mbar_parity >> bi) & 1);
                 mbar_parity ^= 1u << bi;
-                const double *bs = xg + bi * blk;
+                const double *bs = xg + bi * bstr;
                 double *gv = slab + (int64_t)step * blk + voff + own; // v_1..v_s of this step, this thread's column
                 const double t_lo = bs[0];
                 const double dt_s = t_hi - t_lo; // StateStorage::GetDt: difference of the stored times
@@ -516,17 +547,106 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
             // Abar[i][j] += v_m[i] X_{m-1}[j] over all steps and stages; accumulator tile rows FH(k), columns FG(c)
             fence_proxy_async(); // the v sections were written through the generic proxy
             slot_sync();
+#if VA_T8_P3
+            // ---- FP64 tensor instructions. Abar(64 x 64) += V(64 x K) X(K x 64)^T with K = SADJ T (stage, step) pairs. Warp w of the
+            // trajectory owns rows 32 w .. 32 w + 31: 4 x 8 accumulator tiles of 8 x 8 (64 registers per lane, as before), and per
+            // group of four (stage, step) pairs 4 A fragments (v) + 8 B fragments (X) feed 32 DMMAs = 8192 FMAs: 12 LDS.64 where the
+            // DFMA form needs 32 LDS.128 for the same work. DMMA shares the DFMA pipe on B200 (tools/microbench/fp64_mma.cu), so the
+            // gain is load/store-unit relief for the trajectories that sit in their latency-bound phases on the same SM.
+            // Two steps (2 SADJ = 12 stages = 3 groups of four when SADJ = 6) are consumed per iteration: buffers {0,1} / {2,3}.
+            static_assert(NB == 4, "phase 3 works on pairs of step buffers");
+            auto issue3 = [&](int it) { // step T-1-it -> buffer it % NB, vector by vector at the padded stride
+                if (it < T) {
+                    const int bi = it % NB;
+                    const double *src = slab + (int64_t)(T - 1 - it) * blk;
+                    double *dst = xg + bi * bstr;
+                    mbar_expect_tx(&mbar[bi], 2 * SADJ * NP * 8);
+#pragma unroll 1
+                    for (int m = 0; m < SADJ; ++m) {
+                        bulk_g2s(dst + m * VS3, src + HDR + m * NP, NP * 8, &mbar[bi], keep);
+                        bulk_g2s(dst + (SADJ + m) * VS3, src + voff + m * NP, NP * 8, &mbar[bi], keep);
+                    }
+                }
+            };
+            if (tid == 0) { issue3(0); issue3(1); }
+            double C[4][8][2];
+#pragma unroll
+            for (int I = 0; I < 4; ++I)
+#pragma unroll
+                for (int J = 0; J < 8; ++J) C[I][J][0] = C[I][J][1] = 0.0;
+            const int fr = (tid & 31) >> 2, fk = tid & 3; // fragment row / k index of this lane
+            constexpr int NG = (2 * SADJ + 3) / 4;        // groups of four stages per pair of steps
+            for (int it = 0; it < T; it += 2) {
+                const int b0 = it % NB; // buffers b0, b0 + 1 hold steps it, it + 1
+                slot_sync();            // every thread is done with the previous pair: its buffers can be refilled
+                if (tid == 0) { issue3(it + 2); issue3(it + 3); }
+                mbar_wait(&mbar[b0], (mbar_parity >> b0) & 1);
+                mbar_parity ^= 1u << b0;
+                const bool two = it + 1 < T;
+                if (two) {
+                    mbar_wait(&mbar[b0 + 1], (mbar_parity >> (b0 + 1)) & 1);
+                    mbar_parity ^= 1u << (b0 + 1);
+                }
+                const double *pb2 = xg + b0 * bstr;
+#pragma unroll
+                for (int gq = 0; gq < NG; ++gq) {
+                    const int sg = 4 * gq + fk;                 // stage inside the pair handled by this lane's k index
+                    const int st = sg / SADJ, m = sg - st * SADJ; // step inside the pair, stage
+                    const bool valid = sg < 2 * SADJ && (st == 0 || two);
+                    const double *xv = pb2 + (valid ? st * bstr + m * VS3 : 0);
+                    double af[4], bf[8];
+#pragma unroll
+                    for (int I = 0; I < 4; ++I) {
+                        const double v = xv[SADJ * VS3 + 32 * warp + 8 * I + fr];
+                        af[I] = valid ? v : 0.0;
+                    }
+#pragma unroll
+                    for (int J = 0; J < 8; ++J) {
+                        const double v = xv[8 * J + fr];
+                        bf[J] = valid ? v : 0.0;
+                    }
+#pragma unroll
+                    for (int I = 0; I < 4; ++I)
+#pragma unroll
+                        for (int J = 0; J < 8; ++J) dmma(C[I][J][0], C[I][J][1], af[I], bf[J]);
+                }
+            }
+            if (own < n) {
+                if (a.reduce == VA_REDUCE_NONE) mu_o[own] = rbar;
+                else atomicAdd(part + own, rbar);
+            }
+#pragma unroll
+            for (int I = 0; I < 4; ++I) {
+                const int row = 32 * warp + 8 * I + fr;
+#pragma unroll
+                for (int J = 0; J < 8; ++J) {
+                    const int col = 8 * J + 2 * fk;
+                    if (a.reduce == VA_REDUCE_NONE) {
+                        if (EXACT) *reinterpret_cast<double2 *>(mu_o + NP + row * NP + col) = make_double2(C[I][J][0], C[I][J][1]);
+                        else {
+                            if (row < n && col < n) mu_o[n + row * n + col] = C[I][J][0];
+                            if (row < n && col + 1 < n) mu_o[n + row * n + col + 1] = C[I][J][1];
+                        }
+                    } else {
+                        // summed objective: fire-and-forget FP64 reductions into this slot's partial-sum row (one writer per address)
+                        if (row < n && col < n) atomicAdd(part + n + row * n + col, C[I][J][0]);
+                        if (row < n && col + 1 < n) atomicAdd(part + n + row * n + col + 1, C[I][J][1]);
+                    }
+                }
+            }
+        }
+#else
             auto issue3 = [&](int it) {
                 if (it < T) {
                     const int bi = it % NB;
                     const double *src = slab + (int64_t)(T - 1 - it) * blk;
                     if (vsep) {
                         mbar_expect_tx(&mbar[bi], (HDR + 2 * SADJ * NP) * 8);
-                        bulk_g2s(xg + bi * blk, src, (HDR + SADJ * NP) * 8, &mbar[bi], keep);
-                        bulk_g2s(xg + bi * blk + voff, src + voff, SADJ * NP * 8, &mbar[bi], keep);
+                        bulk_g2s(xg + bi * bstr, src, (HDR + SADJ * NP) * 8, &mbar[bi], keep);
+                        bulk_g2s(xg + bi * bstr + voff, src + voff, SADJ * NP * 8, &mbar[bi], keep);
                     } else {
                         mbar_expect_tx(&mbar[bi], xg_bytes);
-                        bulk_g2s(xg + bi * blk, src, xg_bytes, &mbar[bi], keep);
+                        bulk_g2s(xg + bi * bstr, src, xg_bytes, &mbar[bi], keep);
                     }
                 }
             };
@@ -543,7 +663,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 if (tid == 0) issue3(it + NB - 1);
                 mbar_wait(&mbar[bi], (mbar_parity >> bi) & 1);
                 mbar_parity ^= 1u << bi;
-                const double *bs = xg + bi * blk;
+                const double *bs = xg + bi * bstr;
 #pragma unroll
                 for (int m = SADJ; m >= 1; --m) {
                     const double2 *vv = reinterpret_cast<const double2 *>(bs + voff + (m - 1) * NP) + h8;
@@ -591,6 +711,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                     }
             }
         }
+#endif
         slot_sync(); // slab and shared buffers are reused by the next trajectory
     }
 }
@@ -598,7 +719,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 template <class Tab, bool ADAPTIVE, bool EXACT>
 cudaError_t launch_k(const VaGlvWideArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)SLOTS * NB * a.blk_doubles * 8;
+    const size_t smem = (size_t)SLOTS * NB * buf_doubles(a.blk_doubles, Tab::SADJ) * 8;
     cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_glv_t8<Tab, ADAPTIVE, EXACT><<<a.grid, NT, smem, st>>>(a);
@@ -660,7 +781,7 @@ cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *gri
     int sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess) return err;
-    const size_t smem = (size_t)SLOTS * NB * va_glv_t8_block_doubles(stepper, n_out) * 8;
+    const size_t smem = (size_t)SLOTS * NB * buf_doubles(va_glv_t8_block_doubles(stepper, n_out), sadj_of(stepper)) * 8;
     int occ = 0;
     switch (stepper) {
     case VA_RK_RK4: err = occupancy<TabRK4, false>(n, smem, &occ); break;
