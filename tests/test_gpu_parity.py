@@ -270,8 +270,23 @@ def test_glv_half_norm_objective_seeds_and_split_api(va):
         assert len(t) == f["n_accept"][B - 1] + 1 and t[0] == 0.0 and abs(t[-1] - 10.0) < 1e-14
         np.testing.assert_array_equal(x[0], x0[B - 1])
         np.testing.assert_array_equal(x[-1], f["x_final"][B - 1])
-        a = e.adjoint(objective=va.OBJ_HALF_NORM2)
+        a = e.adjoint(objective=va.OBJ_HALF_NORM2)  # B <= resident slots: sweeps back over the step blocks the forward call left
         np.testing.assert_array_equal(a["mu"], r["mu"])
+        np.testing.assert_array_equal(a["lam"], r["lam"])
+        a2 = e.adjoint(objective=va.OBJ_HALF_NORM2)  # and again (the slabs are still valid)
+        np.testing.assert_array_equal(a2["mu"], r["mu"])
+        # more parameter sets than resident slots: the slabs cannot hold them all, the adjoint call re-integrates
+        pb = oracle.synth_params(oracle.SYS_GLV, N, 78, 0, 700)
+        xb = oracle.synth_x0(oracle.SYS_GLV, N, pb)
+        rb = e.forward_adjoint(xb, pb, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM)
+        fb = e.forward(xb, pb, 0.0, 10.0, 1e-3)
+        ab = e.adjoint(objective=va.OBJ_SUM)
+        np.testing.assert_array_equal(fb["x_final"], rb["x_final"])
+        np.testing.assert_array_equal(ab["mu"], rb["mu"])
+        tb, xcb = e.checkpoints(699)  # not in its slot any more: re-integrated on demand
+        assert len(tb) == fb["n_accept"][699] + 1
+        np.testing.assert_array_equal(xcb[0], xb[699])
+        np.testing.assert_array_equal(xcb[-1], fb["x_final"][699])
     # two explicit seeds per trajectory (the reference's SIMD axis): each must match a single-seed oracle sweep
     with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=2) as e:
         r2 = e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds)
@@ -628,6 +643,9 @@ def test_glv_quad_kernel_agrees_with_first_generation_and_oracle(va, monkeypatch
             z = e.forward_adjoint(x0, p, 2.0, 2.0, dt0, objective=va.OBJ_SEED, seeds=seeds)  # ti == tf: no step at all
             e.forward(x0[:50], p[:50], 0.0, tf, dt0)
             t, x = e.checkpoints(min(B, 50) - 1)
+            sa = e.adjoint(objective=va.OBJ_SEED, seeds=seeds[:50])  # split API (runge_kutta, then adjointSolve)
+            np.testing.assert_array_equal(sa["mu"], r["mu"][:50])
+            np.testing.assert_array_equal(sa["lam"], r["lam"][:50])
         with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, ckpt_policy=policy) as e:
             h = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_HALF_NORM2)
             hs = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_HALF_NORM2, reduce=va.REDUCE_SUM)

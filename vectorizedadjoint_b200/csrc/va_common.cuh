@@ -37,6 +37,8 @@ struct VaGlvWideArgs {
     int64_t xstore_stride;
     int seg_len;
     int sparse;           // cluster kernel, recompute policy: keep t_n of every step but x_n only of every seg_len-th (VA_CKPT_SPARSE)
+    int skip_forward;     // va_glv_oct.cu, va_glv_t8.cu: the slabs still hold the forward sweep of exactly these trajectories (split API,
+                          // runge_kutta then adjointSolve): take T, status and x(tf) from n_accept / status / x_final and sweep back only
 };
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);

@@ -154,6 +154,7 @@ struct DevArgs { // all pointers on the device
     int32_t *n_accept, *n_reject, *status;
     bool mu_accumulate; // VA_REDUCE_SUM: add to mu instead of overwriting (chunked host pipeline)
     bool forward_only;
+    bool skip_forward = false; // split API: the slabs still hold the forward sweep of exactly these trajectories
 };
 
 // Runs forward (+ adjoint) for device-resident buffers on stream st.
@@ -190,6 +191,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         }
         a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE || e->desc.ckpt_policy == VA_CKPT_SPARSE;
         a.blk_doubles = e->glv_blk;
+        a.skip_forward = d.skip_forward ? 1 : 0;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
         if (sum && !native_sum && !d.forward_only) {
             // several cost functions per trajectory: per-trajectory gradients into a scratch buffer, then a row reduction
@@ -691,6 +693,7 @@ int va_single_forward(va_engine *e, const va_batch_args *a)
     e->last_ms = ms;
     e->se_B = B; e->se_ti = a->ti; e->se_tf = a->tf; e->se_dt0 = a->dt0;
     e->se_slab_valid = is_glv(e); e->se_ck_b = -1;
+    e->se_blocks_intact = true;
     return VA_OK;
 }
 
@@ -743,8 +746,17 @@ int va_single_adjoint(va_engine *e, const va_batch_args *a)
         d.objective = a->objective; d.reduce = a->reduce; d.x_final = e->se_xf.as<double>(); d.lambda = e->se_lam.as<double>();
         d.mu = e->se_mu.as<double>(); d.n_accept = e->se_acc.as<int32_t>(); d.n_reject = e->se_rej.as<int32_t>();
         d.status = e->se_sta.as<int32_t>(); d.mu_accumulate = false; d.forward_only = false;
+        // runge_kutta then adjointSolve on a batch that fitted one wave of slots (always so for the one-trajectory Driver): the
+        // step blocks / checkpoints of the forward call are still in the slabs, slot b = trajectory b -- sweep back only.
+        // Otherwise the fused kernel re-integrates (deterministic, identical steps).
+        const int64_t slots = e->pairk ? e->grid / e->pair_cl : (int64_t)e->grid * e->tpc;
+        d.skip_forward = e->se_slab_valid && e->se_blocks_intact && B <= slots && e->family == FAM_GLV_WIDE && (e->oct || e->t8) &&
+                         !getenv("VA_SPLIT_REINTEGRATE");
         if (int rc = run_device(e, d, e->s_comp)) return rc;
-        e->se_ck_b = -1; // slot 0 was reused
+        if (!d.skip_forward) { e->se_ck_b = -1; e->se_slab_valid = B <= slots; } // re-integrated: the same first wave is back in the slabs
+        // the store-stages kernels write the seeds v_m over the slopes g_m during the reverse sweep (one seed per trajectory: the two
+        // sections alias): the blocks serve GetTime / GetState afterwards, but not another reverse sweep
+        if (!e->oct) e->se_blocks_intact = false;
     }
     if (sum && e->comm)
         if (int rc = va_comm_allreduce_sum(e, e->se_mu.as<double>(), (int64_t)nout * npar, e->s_comp)) return rc;

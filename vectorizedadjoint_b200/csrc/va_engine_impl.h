@@ -94,6 +94,7 @@ struct va_engine {
     std::vector<int32_t> se_accept_host;
     std::vector<double> se_xf_host;
     bool se_slab_valid = false; // GLV: the slabs still hold the first wave of the session's forward sweep
+    bool se_blocks_intact = false; // ... and no reverse sweep has written into those step blocks yet (they can be swept back once more)
     int64_t se_ck_b = -1;       // GLV: trajectory whose checkpoints were re-integrated into slot 0 for va_get_checkpoints
     int64_t launches = 0;
     double last_ms = 0.0;

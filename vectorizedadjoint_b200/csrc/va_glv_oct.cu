@@ -137,9 +137,18 @@ __global__ void __launch_bounds__(NT, 1) k_glv_oct(const __grid_constant__ VaGlv
         // ================================ forward sweep =====================================
         double t = a.ti, dt = a.dt0, K[S][2];
         int nck = 0, rejects = 0, status = 0, trials = 0;
-        bool act = has && (ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt));
+        bool act = has && !a.skip_forward && (ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt));
         bool fresh = true;
         K[0][0] = K[0][1] = 0.0;
+        if (a.skip_forward && has) {
+            // split API (va_forward_batch then va_adjoint_batch): the checkpoints of this very trajectory are still in the slab
+            nck = a.n_accept[b];
+            status = a.status[b];
+            t = slab[(int64_t)nck * BLK];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (live[k]) x[k] = a.x_final[b * n + own0 + k];
+        }
         while (__any_sync(FULL, act)) {
             // first slope of a step, f(x_n): after every acceptance (dopri5: only for the very first step, afterwards the FSAL
             // slope is reused). All lanes of the warp run the product; only trajectories that need it keep the result.
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_oct(const __grid_constant__ VaGlv
         }
         // close the trajectory: final time, status, x(tf)
         const int T = nck;
-        if (has && o == 0) slab[(int64_t)T * BLK] = t; // header of checkpoint T carries the final time
+        if (has && o == 0 && !a.skip_forward) slab[(int64_t)T * BLK] = t; // header of checkpoint T carries the final time
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (live[k] && !isfinite(x[k])) status |= VA_TRAJ_NONFINITE;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_oct(const __grid_constant__ VaGlv
         status |= __shfl_xor_sync(FULL, status, 4);
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
         const double t_final = t;
-        if (has) {
+        if (has && !a.skip_forward) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (live[k]) a.x_final[b * n + own0 + k] = failed ? nan("") : x[k];

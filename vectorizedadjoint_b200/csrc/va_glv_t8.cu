@@ -331,6 +331,16 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         }
         bool act = ADAPTIVE ? va_less_with_sign(t, tf, dt) : va_less_eq_with_sign(t + dt, tf, dt);
         double *sp = slab + HDR + own; // this thread's column in the current step block (advanced on acceptance)
+        if (a.skip_forward) {
+            // split API (va_forward_batch then va_adjoint_batch): the step blocks of this very trajectory are still in the slab
+            act = false;
+            nck = a.n_accept[b];
+            status = a.status[b];
+            sp += (int64_t)nck * blk;
+            t = sp[-HDR - own];
+            const double xf = a.x_final[b * n + (own < n ? own : 0)];
+            x = own < n ? xf : 0.0;
+        }
 
         while (act) {
             if (fresh) {
@@ -435,14 +445,14 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         }
         // close the trajectory: final time, status, x(tf)
         const int T = nck;
-        if (tid == 0) st_hint(sp - HDR, t, keep); // header of block T carries the final time
+        if (tid == 0 && !a.skip_forward) st_hint(sp - HDR, t, keep); // header of block T carries the final time
         if (own < n && !isfinite(x)) status |= VA_TRAJ_NONFINITE;
         fence_proxy_async(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
         status = slot_or(status);
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
         const double x_tf = x, t_final = t;
-        if (own < n) a.x_final[b * n + own] = failed ? nan("") : x;
-        if (tid == 0) {
+        if (own < n && !a.skip_forward) a.x_final[b * n + own] = failed ? nan("") : x;
+        if (tid == 0 && !a.skip_forward) {
             if (a.n_accept) a.n_accept[b] = T;
             if (a.n_reject) a.n_reject[b] = rejects;
             if (a.status) a.status[b] = status;
