@@ -78,7 +78,14 @@ int ensure_workspace(va_engine *e, int64_t B)
 {
     if (is_glv(e)) {
         const size_t need = (size_t)e->grid * e->tpc * e->pair * e->slab_stride * 8;
+        const void *slab_before = e->slab.p;
         if (int rc = e->slab.ensure(need)) return rc;
+        // a fresh slab is cleared once: idle slots (fewer trajectories than slots, lock-step warps) prefetch block 0 of slabs that
+        // no trajectory has written yet and discard it -- harmless, but it should not be indeterminate memory (initcheck-clean)
+        if (e->slab.p != slab_before) {
+            VA_CUDA(cudaMemsetAsync(e->slab.p, 0, e->slab.bytes, e->s_comp));
+            VA_CUDA(cudaStreamSynchronize(e->s_comp)); // once per allocation; the kernels may run on a caller's stream
+        }
         if (int rc = e->partial.ensure((size_t)e->grid * e->tpc * e->desc.n_par * 8)) return rc;
         if (e->pair_seg)
             if (int rc = e->xstore.ensure((size_t)e->grid * e->xstore_stride * 8)) return rc;

@@ -312,8 +312,9 @@ __global__ void __launch_bounds__(NT, 1) k_glv_oct(const __grid_constant__ VaGlv
             double t_hi = t_final;
             // checkpoint of the first step to process; the next one is fetched while the current one is being worked on
             const double *ckp = slab + (int64_t)(ok && T > 0 ? T - 1 : 0) * BLK;
-            double2 xn_next = *reinterpret_cast<const double2 *>(ckp + HDR + own0);
-            double tn_next = ckp[0];
+            // (idle slots and failed trajectories have no checkpoints to read: their lanes carry zeros through the warp's steps)
+            double2 xn_next = ok ? *reinterpret_cast<const double2 *>(ckp + HDR + own0) : make_double2(0.0, 0.0);
+            double tn_next = ok ? ckp[0] : 0.0;
 #pragma unroll 1
             for (int s = 0; s < Tw; ++s) {
                 const int step = T - 1 - s;
@@ -321,8 +322,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_oct(const __grid_constant__ VaGlv
                 const double xn0 = xn_next.x, xn1 = xn_next.y, t_lo = tn_next;
                 {
                     const double *nx = slab + (int64_t)(ok && step >= 1 ? step - 1 : 0) * BLK;
-                    xn_next = *reinterpret_cast<const double2 *>(nx + HDR + own0);
-                    tn_next = nx[0];
+                    if (ok) {
+                        xn_next = *reinterpret_cast<const double2 *>(nx + HDR + own0);
+                        tn_next = nx[0];
+                    }
                 }
                 const double dt_s = t_hi - t_lo; // StateStorage::GetDt: difference of the stored times
                 // ---- stage recompute from x_n (detail/backpropagation.hpp:24-64): X_m -> shared buffer m, g_m, K_m in registers
