@@ -379,8 +379,11 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
 #pragma unroll
             for (int j = 0; j < m; ++j)
                 if (va_nz_a(SFULL, m, j)) {
+                    // explicit fma: the reverse sweep takes no accept/reject decision, so unlike the forward sweep it need not
+                    // reproduce odeint's rounding; one FP64 instruction per term instead of three (the kernel is FP64-pipe bound)
+                    const double c = dt * tab.a[m * VA_MAX_STAGES + j];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[m * VA_MAX_STAGES + j] * K[j][i];
+                    for (int i = 0; i < N; ++i) xm[i] = fma(c, K[j][i], xm[i]);
                 }
             Sys::rhs(xm, p, time + tab.c[m] * dt, K[m]);
         }
@@ -397,8 +400,9 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
 #pragma unroll
             for (int k = 1; k < m; ++k)
                 if (va_nz_a(SFULL, m - 1, k - 1)) {
+                    const double c = dt * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) xm[i] += dt * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * K[k - 1][i];
+                    for (int i = 0; i < N; ++i) xm[i] = fma(c, K[k - 1][i], xm[i]);
                 }
             Sys::vjp(xm, p, time + tab.c[m - 1] * dt, W[m], gx, mu);
 #pragma unroll
@@ -406,7 +410,7 @@ __device__ __forceinline__ void scalar_adjoint_body(const VaScalarArgs &a)
                 W[0][i] += gx[i];
 #pragma unroll
                 for (int k = 1; k < m; ++k)
-                    if (va_nz_a(SFULL, m - 1, k - 1)) W[k][i] += gx[i] * tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * dt;
+                    if (va_nz_a(SFULL, m - 1, k - 1)) W[k][i] = fma(gx[i], tab.a[(m - 1) * VA_MAX_STAGES + (k - 1)] * dt, W[k][i]);
             }
         }
 #pragma unroll
