@@ -285,7 +285,11 @@ int run_host(va_engine *e, const va_batch_args *a, bool forward_only)
     const bool sum = a->reduce == VA_REDUCE_SUM;
     const int64_t in_bytes = 8LL * (n + npar) + (a->objective == VA_OBJ_SEED ? 8LL * nout * n : 0);
     const int64_t out_bytes = 8LL * n + 8LL * nout * n + (sum ? 0 : 8LL * nout * npar) + 12;
-    const int64_t slot_budget = 2LL << 30;
+    // Chunk size of the pipeline. The copies are the bottleneck (PCIe: 55.6 GB/s against 200+ GB/s of kernel appetite), so what
+    // matters is how soon the first kernel starts and how little is left to compute after the last copy: 512 MB chunks leave
+    // 9 ms + 3 ms outside the copy stream (2 GB chunks: 36 ms + 10 ms of a 655 ms pass). VA_HOST_CHUNK_MB overrides.
+    const char *chunk_env = getenv("VA_HOST_CHUNK_MB");
+    const int64_t slot_budget = (chunk_env && atoll(chunk_env) > 0 ? atoll(chunk_env) : 512LL) << 20;
     int64_t Bc = std::max<int64_t>(1, slot_budget / (in_bytes + out_bytes));
     if (is_glv(e) && Bc > (int64_t)e->grid * e->tpc) Bc = Bc / (e->grid * e->tpc) * (e->grid * e->tpc); // whole waves
     Bc = std::min(Bc, B);
