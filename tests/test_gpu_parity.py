@@ -617,6 +617,70 @@ def test_glv_register_kernel_generations_agree(va, monkeypatch, N, B):
     assert_close(a["mu"].reshape(B * 2, -1), b["mu"].reshape(B * 2, -1), rtol=1e-11, what="mu")
 
 
+@pytest.mark.parametrize("N,B,stepper,adaptive,tol,tf,dt0,n_out", [(64, 1900, 2, True, 1e-8, 10.0, 1e-3, 1), (50, 700, 3, True, 1e-6, 10.0, 1e-3, 2),
+                                                                  (40, 900, 1, False, 0.0, 0.5, 0.01, 1), (64, 3, 2, True, 1e-8, 10.0, 1e-3, 1)])
+def test_glv_warp_specialised_kernel_returns_the_same_bits(va, monkeypatch, N, B, stepper, adaptive, tol, tf, dt0, n_out):
+    """va_glv_t8s.cu (VA_GLV_T8S=1; kept as a measured negative result) runs the sweeps and the gradient
+    accumulation on different warps of the CTA (setmaxnreg register split, job queue, two slab halves per slot) but forms every sum
+    in the order of va_glv_t8.cu: per-trajectory results, the summed gradient, the split API and the checkpoints must be
+    bit-identical -- with several trajectories per slot (both slab halves, the queue under load), padded species counts, two seeds
+    (synchronous hand-over), fixed-step rk4, dopri5 and fewer trajectories than slots."""
+    p = oracle.synth_params(oracle.SYS_GLV, N, 4242, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(5).standard_normal((B, n_out, N))
+    res = []
+    for spec in (False, True):
+        if spec:
+            monkeypatch.setenv("VA_GLV_T8S", "1")
+        with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, n_out=n_out) as e:
+            assert e.info()["kernel_name"] == ("k_glv_t8s" if spec else "k_glv_t8")
+            r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds)
+            s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM)
+            e.forward(x0, p, 0.0, tf, dt0)
+            ck = e.checkpoints(min(B - 1, 2))
+            a = e.adjoint(objective=va.OBJ_SEED, seeds=seeds)
+        assert (r["status"] == 0).all()
+        res.append((r, s, ck, a))
+    (r0, s0, ck0, a0), (r1, s1, ck1, a1) = res
+    for k in ("x_final", "lam", "mu", "n_accept", "n_reject"):
+        np.testing.assert_array_equal(r0[k], r1[k], err_msg=k)
+    np.testing.assert_array_equal(s0["mu"], s1["mu"])
+    np.testing.assert_array_equal(ck0[0], ck1[0])
+    np.testing.assert_array_equal(ck0[1], ck1[1])
+    np.testing.assert_array_equal(a0["mu"], a1["mu"])
+    np.testing.assert_array_equal(a1["mu"], r1["mu"])  # split API == fused call
+    # and against the oracle on a few sets (the second-generation kernel is checked against it everywhere else)
+    nb = min(B, 3)
+    o = oracle.forward_adjoint(oracle.SYS_GLV, N, stepper, adaptive, tol, tol, x0[:nb], p[:nb], 0.0, tf, dt0, objective=oracle.OBJ_SEED,
+                               seeds=seeds[:nb, 0], threads=2)
+    np.testing.assert_array_equal(r1["n_accept"][:nb], o["n_accept"])
+    assert_close(r1["mu"][:nb, 0], o["mu"], what="mu vs oracle")
+
+
+def test_glv64_dead_step_blocks_dropped_from_l2_change_nothing(va, monkeypatch):
+    """VA_T8_DISCARD=1: with more trajectories than slots the headline kernel drops the L2 lines of a trajectory's step blocks once its
+    gradient accumulation has read them (discard.global.L2; -30 % DRAM traffic, -1.1 % rate, hence opt-in). The blocks are dead by
+    then: every result must be bit-identical, in both gradient modes and with two seeds (blocks reused by the second seed)."""
+    N, B = 64, 2500
+    p = oracle.synth_params(oracle.SYS_GLV, N, 99, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    seeds = np.random.default_rng(6).standard_normal((B, 2, N))
+    res = []
+    for drop in (False, True):
+        if drop:
+            monkeypatch.setenv("VA_T8_DISCARD", "1")
+        out = []
+        for n_out in (1, 2):
+            with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8, n_out=n_out) as e:
+                assert e.info()["kernel_name"] == "k_glv_t8"
+                out.append(e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SEED, seeds=seeds[:, :n_out]))
+                out.append(e.forward_adjoint(x0, p, 0.0, 10.0, 1e-3, objective=va.OBJ_SUM, reduce=va.REDUCE_SUM))
+        res.append(out)
+    for a, b in zip(*res):
+        for k in ("x_final", "lam", "mu", "n_accept"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
 @pytest.mark.parametrize("N,B,stepper,adaptive,tol,tf,dt0", [(16, 300, 2, True, 1e-8, 10.0, 1e-3), (16, 40, 3, True, 1e-6, 10.0, 1e-3),
                                                             (10, 37, 2, True, 1e-8, 10.0, 1e-3), (13, 9, 3, True, 1e-7, 10.0, 1e-3),
                                                             (5, 33, 2, True, 1e-5, 10.0, 1e-3), (16, 21, 1, False, 0.0, 0.3, 0.01),

@@ -40,6 +40,9 @@ struct VaGlvWideArgs {
     int skip_forward;     // va_glv_oct.cu, va_glv_t8.cu: the slabs still hold the forward sweep of exactly these trajectories (split API,
                           // runge_kutta then adjointSolve): take T, status and x(tf) from n_accept / status / x_final and sweep back only
 };
+// VaGlvWideArgs::flags, va_glv_t8.cu: the step blocks are dead once the gradient accumulation has read them (the batch is larger than
+// one wave of slots, so no later call can use the slabs): drop their L2 lines instead of letting them be written back
+#define VA_GLV_FLAG_DISCARD 0x100
 bool va_glv_wide_supported(int n, int stepper, int adaptive);
 int64_t va_glv_wide_slab_doubles(int n, int stepper, int cap);
 int va_glv_wide_pair();                            // trajectories a slot integrates forward together (slabs per slot)
@@ -51,8 +54,17 @@ cudaError_t va_glv_wide_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st)
 // second-generation register kernel for 33..64 species (va_glv_t8.cu): 64 threads per trajectory, 8x8 tiles, three phases
 bool va_glv_t8_supported(int n, int stepper, int adaptive);
 int va_glv_t8_block_doubles(int stepper, int n_out);
+int va_glv_t8_header_doubles();
 cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);
 cudaError_t va_glv_t8_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
+
+// third generation for 33..64 species (va_glv_t8s.cu): sweeps and gradient accumulation on different warps (setmaxnreg register
+// split, job queue between them); a slot's slab has two halves of (cap + 1) step blocks
+bool va_glv_t8s_supported(int n, int stepper, int adaptive);
+int va_glv_t8s_block_doubles(int stepper, int n_out);
+int64_t va_glv_t8s_slab_doubles(int stepper, int n_out, int cap);
+cudaError_t va_glv_t8s_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta);
+cudaError_t va_glv_t8s_forward_adjoint(const VaGlvWideArgs &a, cudaStream_t st);
 
 // quad kernel for up to 16 species (va_glv_quad.cu): four lanes per trajectory, eight trajectories per warp, three phases
 bool va_glv_quad_supported(int n, int stepper, int adaptive);

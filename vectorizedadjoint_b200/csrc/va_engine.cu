@@ -199,6 +199,11 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         a.recompute = e->desc.ckpt_policy == VA_CKPT_RECOMPUTE || e->desc.ckpt_policy == VA_CKPT_SPARSE;
         a.blk_doubles = e->glv_blk;
         a.skip_forward = d.skip_forward ? 1 : 0;
+        // VA_T8_DISCARD=1 (measured trade, off by default): with more trajectories than slots every slab is reused inside this launch
+        // and serves no later call, so the headline kernel may drop its dead step blocks from L2 instead of letting them be written
+        // back -- DRAM traffic 184 -> 128 GB per 2^20 sets (5.0 x -> 3.5 x the compulsory bytes) at 1.1 % fewer gradients/s
+        if (e->family == FAM_GLV_WIDE && e->t8 && !e->t8s && d.B > (int64_t)e->grid * e->tpc && getenv("VA_T8_DISCARD") && atoi(getenv("VA_T8_DISCARD")) != 0)
+            a.flags |= VA_GLV_FLAG_DISCARD;
         const bool native_sum = sum && nout == 1 && !d.forward_only;
         if (sum && !native_sum && !d.forward_only) {
             // several cost functions per trajectory: per-trajectory gradients into a scratch buffer, then a row reduction
@@ -211,6 +216,7 @@ int run_device(va_engine *e, const DevArgs &d, cudaStream_t st)
         }
         if (e->family == FAM_GLV_WIDE && e->oct) VA_CUDA(va_glv_oct_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE && e->quad) VA_CUDA(va_glv_quad_forward_adjoint(a, st));
+        else if (e->family == FAM_GLV_WIDE && e->t8s) VA_CUDA(va_glv_t8s_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE && e->t8) VA_CUDA(va_glv_t8_forward_adjoint(a, st));
         else if (e->family == FAM_GLV_WIDE) VA_CUDA(va_glv_wide_forward_adjoint(a, st));
         else if (e->pairk) VA_CUDA(va_glv_pair_forward_adjoint(a, st));
@@ -566,15 +572,23 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
                 while (e->grid > 1 && (double)e->grid * e->tpc * e->slab_stride * 8.0 > frac * (double)free_b) e->grid = (e->grid + 1) / 2;
             }
         } else if (e->t8) {
-            ce = va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
+            // third generation (va_glv_t8s.cu); VA_GLV_T8S=1 selects it
+            e->t8s = va_glv_t8s_supported(desc->n_state, desc->stepper, desc->adaptive) && getenv("VA_GLV_T8S") && atoi(getenv("VA_GLV_T8S")) != 0;
+            if (e->t8s && va_glv_t8s_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc) != cudaSuccess) {
+                cudaGetLastError();
+                e->t8s = false; // step blocks too large for its shared-memory rings (several seeds per trajectory on a long tableau)
+            }
+            ce = e->t8s ? cudaSuccess
+                        : va_glv_t8_config(desc->n_state, desc->stepper, desc->n_out, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
             e->pair = 1;
             e->glv_blk = va_glv_t8_block_doubles(desc->stepper, desc->n_out);
+            e->glv_hdr = va_glv_t8_header_doubles();
             // the kernel marks its checkpoint slabs evict_last: give that class the largest L2 share the device allows
             int max_persist = 0;
             if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device) == cudaSuccess && max_persist > 0)
                 persist_l2_acquire(e, (size_t)max_persist);
             if (getenv("VA_DEBUG")) fprintf(stderr, "va: persisting L2 limit %d bytes\n", max_persist);
-            e->slab_stride = (int64_t)(e->cap + 1) * e->glv_blk;
+            e->slab_stride = e->t8s ? va_glv_t8s_slab_doubles(desc->stepper, desc->n_out, e->cap) : (int64_t)(e->cap + 1) * e->glv_blk;
         } else {
             ce = va_glv_wide_config(desc->n_state, desc->stepper, e->device, &e->grid, &e->ctas_per_sm, &e->threads, &e->tpc);
             e->pair = va_glv_wide_pair();
@@ -639,7 +653,7 @@ static int single_get_info(va_engine *e, va_engine_info *info)
     info->chunk_trajectories = e->chunk_traj;
     info->kernel_launches = e->launches;
     info->last_kernel_ms = e->last_ms;
-    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->oct ? "k_glv_oct" : e->quad ? "k_glv_quad" : e->t8 ? "k_glv_t8" : "k_glv_wide")
+    const char *kn = e->family == FAM_SCALAR ? "k_scalar" : e->family == FAM_TAPE ? "jit" : e->family == FAM_GLV_WIDE ? (e->oct ? "k_glv_oct" : e->quad ? "k_glv_quad" : e->t8s ? "k_glv_t8s" : e->t8 ? "k_glv_t8" : "k_glv_wide")
                      : e->pairk ? "k_glv_pair" : e->ring ? "k_glv_ring" : "k_glv_stream";
     std::snprintf(info->kernel_name, sizeof(info->kernel_name), "%s", kn);
     cudaDeviceProp prop;
@@ -846,7 +860,7 @@ int va_single_get_checkpoints(va_engine *e, int64_t b, int32_t capacity, double 
                                                                 : va_glv_stream_block_doubles(n, e->desc.stepper, e->desc.ckpt_policy == VA_CKPT_RECOMPUTE)) * 8;
         if (t) VA_CUDA(cudaMemcpy2D(t, 8, base, pitch, 8, (size_t)T + 1, cudaMemcpyDeviceToHost));
         if (x) {
-            if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + 8, pitch, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));
+            if (T > 0) VA_CUDA(cudaMemcpy2D(x, (size_t)n * 8, base + e->glv_hdr, pitch, (size_t)n * 8, (size_t)T, cudaMemcpyDeviceToHost));
             std::memcpy(x + (size_t)T * n, e->se_xf_host.data() + (size_t)b * n, (size_t)n * 8);
         }
     }

@@ -66,9 +66,11 @@ struct va_engine {
     // wide family
     int grid = 0, ctas_per_sm = 0, threads = 0, tpc = 1, pair = 1; // tpc: slots per CTA; pair: slabs per slot
     bool t8 = false;  // FAM_GLV_WIDE served by va_glv_t8.cu (33..64 species)
+    bool t8s = false; // ... by its third generation va_glv_t8s.cu (sweep / accumulate warps); implies t8
     bool quad = false; // FAM_GLV_WIDE served by va_glv_quad.cu (up to 16 species, store-stages policy)
     bool oct = false;  // FAM_GLV_WIDE served by va_glv_oct.cu (up to 16 species, recompute policy: the default there)
     int glv_blk = 0;  // doubles per step block of the register-kernel slab
+    int glv_hdr = 8;  // doubles in front of the stage states of a step block (header[0] = t_n)
     bool ring = false; // FAM_GLV_STREAM served by va_glv_ring.cu (256 species, store-stages policy)
     int ring_flags = 0;
     bool pairk = false; // FAM_GLV_STREAM served by va_glv_pair.cu (256 species, matrix on chip in a cluster of pair_cl CTAs)

@@ -100,6 +100,12 @@ using va_tma::mbar_wait;
 using va_tma::fence_proxy_async;
 using va_tma::ldg_hint;
 __device__ __forceinline__ void st_hint(double *p, double v, uint64_t policy) { va_tma::st_hint_relaxed(p, v, policy); }
+// A step block is dead once the gradient accumulation has copied it to shared memory, but its L2 lines are dirty: when the next
+// trajectory of the slot does not overwrite them before they are evicted, each costs a DRAM write of data nobody will read.
+// discard.L2 drops a line without the write-back. Measured (2^20 sets): DRAM traffic 184 -> 128 GB per launch, 5.95 -> 5.88 M
+// gradients/s whether the discards sit inside the accumulation loop or behind it -- the kernel is bound by the FP64 pipe, not by
+// DRAM, so the engine only asks for it under VA_T8_DISCARD=1.
+__device__ __forceinline__ void discard_line(const double *p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 
 // max over the warp of non-negative doubles (or NaN, which orders above everything): two 32-bit redux operations on
 // the bit pattern instead of five double shuffles + DMNMX
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     const int voff = blk - SADJ * NP;                        // v section of a step block
     const uint32_t xg_bytes = (HDR + 2 * SADJ * NP) * 8;     // header, X and g
     const bool vsep = voff != HDR + SADJ * NP;               // v has its own section (several seeds per trajectory)
+    const bool drop_blocks = (a.flags & VA_GLV_FLAG_DISCARD) != 0; // the slabs will not be read after this call (batch > one wave of slots)
     const int64_t gslot = (int64_t)blockIdx.x * SLOTS + slot; // global slot: owns one slab and one partial-sum row
     double *const slab = a.slab + gslot * a.slab_stride;
     const int bstr = buf_doubles(blk, SADJ); // doubles per shared-memory step buffer
@@ -691,6 +698,13 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                         for (int c = 0; c < 8; ++c) Ab[k][c] = fma(vr[k], xc[c], Ab[k][c]);
                 }
             }
+            if (drop_blocks && o == a.n_out - 1) {
+                // last use of this trajectory's step blocks: drop the 128-byte lines that lie completely inside blocks 0..T-1 (a block
+                // is 6208 bytes, so the slab's first and last touched lines may be shared with the header of block T: left alone)
+                const uintptr_t lo = (reinterpret_cast<uintptr_t>(slab) + 127) & ~(uintptr_t)127;
+                const uintptr_t hi_ = (reinterpret_cast<uintptr_t>(slab + (int64_t)T * blk)) & ~(uintptr_t)127;
+                for (uintptr_t p = lo + (uintptr_t)tid * 128; p < hi_; p += (uintptr_t)NTT * 128) discard_line(reinterpret_cast<const double *>(p));
+            }
             if (a.reduce == VA_REDUCE_NONE) {
                 if (own < n) mu_o[own] = rbar;
 #pragma unroll
@@ -785,6 +799,7 @@ bool va_glv_t8_supported(int n, int stepper, int adaptive)
 
 // step block: [8-double header | X_0..X_{s-1} | g_0..g_{s-1} | v_1..v_s]; with one seed per trajectory v aliases g
 int va_glv_t8_block_doubles(int stepper, int n_out) { return HDR + (n_out > 1 ? 3 : 2) * sadj_of(stepper) * NP; }
+int va_glv_t8_header_doubles() { return HDR; }
 
 cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *grid, int *ctas_per_sm, int *threads, int *slots_per_cta)
 {
