@@ -676,7 +676,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 for (int c = 0; c < 8; ++c) Ab[k][c] = 0.0;
             for (int it = 0; it < T; ++it) {
                 const int bi = it % NB;
-                slot_sync(); // every thread is done with iteration it-1: its buffer can be refilled
+                // every thread is done with iteration it-1: its buffer can be refilled. (Measured alternative: a per-buffer
+                // "released" mbarrier with one arrival per warp instead of this 64-thread barrier, so that the two warps of the
+                // slot need not meet once per step -- 5.83 M against 5.95 M gradients/s: the warps drifting apart costs more than
+                // the barrier, tools/gpu_r2_p3sync.sh.)
+                slot_sync();
                 if (tid == 0) issue3(it + NB - 1);
                 mbar_wait(&mbar[bi], (mbar_parity >> bi) & 1);
                 mbar_parity ^= 1u << bi;
