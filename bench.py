@@ -99,11 +99,11 @@ def cpu_run(sample, threads):
 
 
 def _calibrate(cores):
-    """gradients/s of the CPU path from two short runs; the difference cancels the one-off cost (AADC records and
-    JIT-compiles the RHS once per thread, ~0.2 s at N=64)."""
-    t1, _ = cpu_run(2 * cores, cores)
-    t2, _ = cpu_run(6 * cores, cores)
-    return 4 * cores / max(t2 - t1, 1e-3)
+    """gradients/s of the CPU path from one run of about a second (128 parameter sets per thread). It includes the one-off cost
+    (AADC records and JIT-compiles the RHS once per thread, ~0.2 s at N=64), so it errs low and the sample sized from it runs
+    10-15 s. (Round 2: two runs of 2 and 6 sets per thread and their difference were too short to time -- 9632 sets, 4.4 s.)"""
+    t, _ = cpu_run(128 * cores, cores)
+    return 128 * cores / max(t, 1e-3)
 
 
 def cpu_baseline(sample=0):

@@ -15,6 +15,29 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle
 import vectorizedadjoint_b200 as va
 
+# round 2, second session: the warp-specialised 33..64-species kernel (setmaxnreg, job queue, two slab halves) and the L2 discards
+# of the second generation, on two persistent CTAs so that every slot integrates several trajectories
+for env, N, stepper, adaptive, tol, n_out, B in [({"VA_GLV_T8S": "1"}, 64, va.RK_CK54, True, 1e-6, 1, 29), ({"VA_GLV_T8S": "1"}, 50, va.RK_DOPRI5, True, 1e-5, 2, 19),
+                                                 ({"VA_GLV_T8S": "1"}, 40, va.RK_RK4, False, 0.0, 1, 21), ({"VA_T8_DISCARD": "1"}, 64, va.RK_CK54, True, 1e-6, 1, 29),
+                                                 ({"VA_T8_DISCARD": "1"}, 50, va.RK_CK54, True, 1e-6, 2, 19)]:
+    os.environ.update(env)
+    os.environ["VA_GLV_MAX_CTAS"] = "2"
+    p = oracle.synth_params(oracle.SYS_GLV, N, 8, 0, B)
+    x0 = oracle.synth_x0(oracle.SYS_GLV, N, p)
+    tf, dt0 = (10.0, 1e-3) if adaptive else (0.2, 0.01)
+    seeds = np.random.default_rng(0).standard_normal((B, n_out, N))
+    with va.Engine(va.SYS_GLV, N, stepper, adaptive, tol, tol, n_out=n_out) as e:
+        r = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds)
+        s = e.forward_adjoint(x0, p, 0.0, tf, dt0, objective=va.OBJ_SEED, seeds=seeds, reduce=va.REDUCE_SUM)
+        info = e.info()
+    for k in list(env) + ["VA_GLV_MAX_CTAS"]:
+        os.environ.pop(k)
+    assert (r["status"] == 0).all()
+    np.testing.assert_allclose(s["mu"], r["mu"].sum(axis=0), rtol=1e-10, atol=1e-300)
+    print(N, info["kernel_name"], env, "ctas", info["grid"] if "grid" in info else "?", "steps", r["n_accept"].tolist(), flush=True)
+if os.environ.get("VA_SANITIZE_ONLY") == "t8s":
+    print("sanitize: t8s / discard section only")
+    sys.exit(0)
 for N, stepper, adaptive, tol, n_out, B in [(64, va.RK_CK54, True, 1e-6, 1, 9), (50, va.RK_DOPRI5, True, 1e-5, 2, 5), (64, va.RK_RK4, False, 0.0, 1, 3),
                                             (16, va.RK_CK54, True, 1e-6, 1, 9), (10, va.RK_CK54, True, 1e-6, 2, 7), (5, va.RK_DOPRI5, True, 1e-6, 1, 3),
                                             (20, va.RK_RK4, False, 0.0, 1, 3), (33, va.RK_CK54, True, 1e-5, 1, 3), (100, va.RK_CK54, True, 1e-5, 1, 2),

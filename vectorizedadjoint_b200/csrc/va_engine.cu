@@ -596,6 +596,9 @@ int va_single_create(const va_engine_desc *desc, va_engine **out)
             e->slab_stride = va_glv_wide_slab_doubles(desc->n_state, desc->stepper, e->cap);
         }
         if (ce != cudaSuccess) return bail(VA_E_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(ce));
+        // test knob: fewer persistent CTAs, so that a small batch (compute-sanitizer runs) gives every slot several trajectories
+        if (const char *env = getenv("VA_GLV_MAX_CTAS"))
+            if (atoi(env) >= 1) e->grid = std::min(e->grid, atoi(env));
         e->desc.ckpt_policy = e->oct ? VA_CKPT_RECOMPUTE : VA_CKPT_STORE_STAGES;
     } else {
         e->threads = 128;

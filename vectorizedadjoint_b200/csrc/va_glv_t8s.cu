@@ -77,17 +77,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ int ld_volatile_s32(const int *p)
-{
-    int v;
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_s32(int *p, int v)
-{
-    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-
 // max over the warp of non-negative doubles (or NaN, which orders above everything): two 32-bit redux operations
 __device__ __forceinline__ double warp_max_nonneg(double e)
 {
@@ -119,7 +108,7 @@ struct SharedState {
     int st[SLOTS][2];
     uint64_t mbar[SLOTS][NB]; // phase 2: step block landed
     uint64_t abar[NBA];       // accumulate ring: step block landed
-    uint64_t ebar[NBA];       // accumulate ring: buffer released by the four accumulate warps
+    uint64_t ebar[NBA];       // accumulate ring: buffer released by the 128 accumulate threads
     uint64_t qbar[QN];        // job queue: entry written
     int qe[QN][8];            // {slot | exit flag, steps, slab half, seed, trajectory lo, trajectory hi}
     int q_tail;
@@ -155,7 +144,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_t8s(const __grid_constant__ VaGlv
 #pragma unroll
         for (int i = 0; i < NBA; ++i) {
             mbar_init(&sh.abar[i], 1);
-            mbar_init(&sh.ebar[i], NAC / 32);
+            mbar_init(&sh.ebar[i], NAC);
         }
 #pragma unroll
         for (int i = 0; i < QN; ++i) mbar_init(&sh.qbar[i], 1);
@@ -207,9 +196,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_t8s(const __grid_constant__ VaGlv
             slot_sync();
             return sh.st[slot][0] | sh.st[slot][1];
         };
-        // the accumulate warps have finished `target` jobs of this slot (volatile poll; satisfied on arrival in the common case)
+        // the accumulate warps have finished `target` jobs of this slot (satisfied on arrival in the common case). The counter is
+        // read and written with shared-memory atomics only: a flag protocol, not a data race
         auto wait_done = [&](int target) {
-            while (ld_volatile_s32(&sh.done[slot]) < target) __nanosleep(200);
+            while (atomicAdd(&sh.done[slot], 0) < target) __nanosleep(200);
         };
         auto post = [&](int slot_flags, int T, int half, int o, int64_t b) {
             const int tk = atomicAdd(&sh.q_tail, 1);
@@ -561,7 +551,7 @@ __global__ void __launch_bounds__(NT, 1) k_glv_t8s(const __grid_constant__ VaGlv
         auto issue3 = [&](const double *src) {
             const uint32_t k = n_issued++;
             const int bj = k % NBA;
-            if (k >= NBA) mbar_wait(&sh.ebar[bj], ((k / NBA) - 1) & 1); // the four warps have released the block that was there
+            if (k >= NBA) mbar_wait(&sh.ebar[bj], ((k / NBA) - 1) & 1); // every accumulate thread has released the block that was there
             double *dst = ring + (size_t)bj * blk;
             if (vsep) {
                 mbar_expect_tx(&sh.abar[bj], (HDR + 2 * SADJ * NP) * 8);
@@ -618,11 +608,10 @@ __global__ void __launch_bounds__(NT, 1) k_glv_t8s(const __grid_constant__ VaGlv
 #pragma unroll
                         for (int c = 0; c < 4; ++c) Ab[k][c] = fma(vr[k], xc[c], Ab[k][c]);
                 }
-                __syncwarp();
-                if ((at & 31) == 0) mbar_arrive(&sh.ebar[bi]); // this warp is done with the buffer
+                mbar_arrive(&sh.ebar[bi]); // this thread is done with the buffer (released when all 128 have arrived)
             }
             // every block of the job has landed (thread 0 waited for each): the slot may overwrite this half of its slab
-            if (at == 0) st_volatile_s32(&sh.done[slot], ld_volatile_s32(&sh.done[slot]) + 1);
+            if (at == 0) atomicAdd(&sh.done[slot], 1);
             if (a.reduce == VA_REDUCE_NONE) {
                 double *mu_o = a.mu + (b * a.n_out + o) * npar;
 #pragma unroll
