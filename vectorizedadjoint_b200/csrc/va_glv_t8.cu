@@ -49,6 +49,9 @@
 #ifndef VA_T8_MAP
 #define VA_T8_MAP 0 // warp -> trajectory map inside a CTA (see the kernel)
 #endif
+#ifndef VA_T8_STAGE
+#define VA_T8_STAGE 1 // one seed per trajectory: the parameter set [r, A] is brought into shared memory by one TMA bulk copy (see the kernel)
+#endif
 #ifndef VA_T8_P3
 #define VA_T8_P3 0 // phase 3 (Abar += v x^T): 0 = DFMA on 8x8 register tiles, 1 = FP64 tensor instructions (DMMA m8n8k4), see the kernel
 #endif
@@ -63,6 +66,8 @@ constexpr int MINB = SLOTS == 1 ? VA_T8_MINB : 1;
 
 constexpr int HDR = 8;  // doubles in a step-block header (hdr[0] = t_n)
 constexpr int NB = VA_T8_P3 ? 4 : VA_T8_NB;
+constexpr int NB_STAGED = 3;          // step-block buffers per slot when the parameter sets are staged (shared memory: 4 x 3 x 6.2 KB + 4 x 32.5 KB)
+constexpr int PA_DOUBLES = NP * NP + NP; // shared-memory copy of one parameter set
 // DMMA variant of phase 3: a step's 2 x SADJ vectors sit in shared memory with a stride of 68 doubles (544 B = 32 B more than a
 // multiple of 128), so that the fragment loads -- lane l reads element (l >> 2) of vector (l & 3): four vectors, 32 bytes each
 // per half-warp -- touch every bank once; with the natural stride of 512 B they were 4-way bank conflicts
@@ -135,9 +140,17 @@ __device__ __forceinline__ double inv_root_short(double e)
     return y;
 }
 
-template <class Tab, bool ADAPTIVE, bool EXACT>
+// STAGE (one seed per trajectory; round 2, second session): the parameter set of a trajectory is copied to shared memory by ONE TMA
+// bulk copy, issued as soon as the previous trajectory of the slot has taken its second (transposed) matrix tile, i.e. a whole
+// reverse sweep ahead of its use. Both register tiles are then cut from shared memory. Before, each tile was gathered from
+// global memory / L2 by per-lane loads that touch 32 (row-major tile) and 8 (transposed tile) different 128-byte lines per warp
+// instruction -- 1500 L1 tag requests per warp and trajectory, a tenth of all load/store-unit work of this kernel, whose LSU is as
+// busy as its FP64 pipe -- and the parameters had to survive in L2 from the forward sweep to the reverse sweep. Costs one of the
+// four step-block buffers per slot (shared memory).
+template <class Tab, bool ADAPTIVE, bool EXACT, bool STAGE>
 __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaGlvWideArgs a)
 {
+    constexpr int NB = STAGE ? NB_STAGED : ::NB; // step-block buffers per slot in THIS instantiation
     constexpr int S = Tab::S, SADJ = Tab::SADJ;
     constexpr int SE = Tab::FSAL ? S - 1 : S; // stages evaluated through an intermediate state
     extern __shared__ __align__(128) double xg_all[]; // per slot: NB step-block buffers of a.blk_doubles
@@ -145,6 +158,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     __shared__ double red_all[SLOTS][2];
     __shared__ int st_all[SLOTS][2];
     __shared__ __align__(8) uint64_t mbar_all[SLOTS][NB];
+    __shared__ __align__(8) uint64_t pbar_all[SLOTS]; // STAGE: the slot's parameter set has landed
 
     // Warp w of the CTA runs on SM sub-partition w % 4 (tools/microbench/smsp_map.cu). Slot s takes the warp pair
     // {2 s, 2 s + 1}: the two warps of a trajectory sit on different sub-partitions, and every sub-partition hosts one warp of
@@ -182,6 +196,16 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     double(*xs)[NP] = xs_all[slot];
     double *red = red_all[slot];
     uint64_t *mbar = mbar_all[slot];
+    uint64_t *const pbar = &pbar_all[slot];
+    // STAGE: this slot's copy of the current parameter set, behind the step-block buffers of all slots
+    double *const pa = xg_all + (size_t)SLOTS * NB * bstr + (size_t)slot * PA_DOUBLES;
+    const int64_t bstride = (int64_t)gridDim.x * SLOTS; // trajectories between two of this slot
+    auto fetch_params = [&](int64_t bb) { // one thread of the slot, after every thread's last read of `pa`
+        if (bb < a.B) {
+            mbar_expect_tx(pbar, (uint32_t)npar * 8u);
+            bulk_g2s(pa, a.params + bb * npar, (uint32_t)npar * 8u, pbar, policy_evict_first());
+        }
+    };
     const double tf = a.tf;
     const uint64_t keep = policy_evict_last();
 
@@ -209,9 +233,10 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) mbar_init(&mbar[i], 1);
+        mbar_init(pbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    uint32_t mbar_parity = 0; // bit i: parity of the next completion of mbar[i]
+    uint32_t mbar_parity = 0; // bit i: parity of the next completion of mbar[i]; bit 16: of pbar
 
     // summed mode: this slot's partial-sum row; every thread zeroes exactly the entries it later adds to
     double *const part = a.partial + gslot * npar;
@@ -238,6 +263,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 #endif
     }
     __syncthreads();
+    if (STAGE && tid == 0) fetch_params(gslot); // the slot's first parameter set
 
     // y_own = sum_c M[k][c] xin[FG(c)] summed over the group; M is held permuted (register row k <-> tile row k ^ g): lane
     // g ^ j keeps the partial sum of lane g's row in register j, so the group sum is ONE round of 7 independent double
@@ -295,15 +321,19 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         const double *pb = a.params + b * npar;
         double M[RT][CT];
         // ================================ phase 1: forward sweep =====================================
+        if (STAGE) { // the parameter set was requested a reverse sweep ago
+            mbar_wait(pbar, (mbar_parity >> 16) & 1);
+            mbar_parity ^= 1u << 16;
+        }
         // tile rows RT hi + (k ^ g), columns FG(c)
 #pragma unroll
         for (int k = 0; k < RT; ++k) {
             const int row = RT * hi + (k ^ g);
             if (EXACT) {
-                const double2 *src = reinterpret_cast<const double2 *>(pb + NP + row * NP);
+                const double2 *src = reinterpret_cast<const double2 *>((STAGE ? pa : pb) + NP + row * NP);
 #pragma unroll
                 for (int j = 0; j < CT / 2; ++j) {
-                    const double2 v = __ldg(src + PO(j));
+                    const double2 v = STAGE ? src[PO(j)] : __ldg(src + PO(j));
                     M[k][2 * j] = v.x;
                     M[k][2 * j + 1] = v.y;
                 }
@@ -315,7 +345,8 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                         // padded entries: the load goes to a valid address and is discarded (the compiler may turn a guarded
                         // load into load + select, which must not leave the parameter block)
                         const bool in = row < n && col < n;
-                        const double v = __ldg(pb + n + (in ? row * n + col : 0));
+                        const int at = n + (in ? row * n + col : 0);
+                        const double v = STAGE ? pa[at] : __ldg(pb + at);
                         M[k][c] = in ? v : 0.0;
                     }
                 }
@@ -324,7 +355,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         double r_own = 0.0, x = 0.0;
         {
             const int oi = own < n ? own : 0; // padded lanes read a valid address and discard it
-            const double rv = __ldg(pb + oi), xv0 = __ldg(a.x0 + b * n + oi);
+            const double rv = STAGE ? pa[oi] : __ldg(pb + oi), xv0 = __ldg(a.x0 + b * n + oi);
             if (own < n) { r_own = rv; x = xv0; }
         }
 
@@ -464,7 +495,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
             if (a.n_reject) a.n_reject[b] = rejects;
             if (a.status) a.status[b] = status;
         }
-        if (a.n_out <= 0) continue;
+        if (a.n_out <= 0 || (STAGE && failed)) {
+            // no reverse sweep will read the staged parameter set (the barrier inside slot_or is behind every thread's reads of it)
+            if (STAGE && tid == 0) fetch_params(b + bstride);
+            if (a.n_out <= 0) continue;
+        }
 
         // ================================ phase 2: adjoint of the state =====================================
         for (int o = 0; o < a.n_out; ++o) {
@@ -485,10 +520,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 #pragma unroll
                 for (int k = 0; k < RT; ++k) {
                     const int col = RT * hi + (k ^ g);
-                    if (EXACT) M[k][c] = ldg_hint(pb + NP + row * NP + col, drop);
+                    if (EXACT) M[k][c] = STAGE ? pa[NP + row * NP + col] : ldg_hint(pb + NP + row * NP + col, drop);
                     else {
                         const bool in = row < n && col < n;
-                        const double v = ldg_hint(pb + n + (in ? row * n + col : 0), drop);
+                        const int at = n + (in ? row * n + col : 0);
+                        const double v = STAGE ? pa[at] : ldg_hint(pb + at, drop);
                         M[k][c] = in ? v : 0.0;
                     }
                 }
@@ -507,9 +543,11 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                     bulk_g2s(xg + bi * bstr, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi], keep);
                 }
             };
-            slot_sync(); // every thread is past its reads of the buffers (previous seed / trajectory)
-            if (tid == 0)
+            slot_sync(); // every thread is past its reads of the buffers (previous seed / trajectory) -- and of the staged parameters
+            if (tid == 0) {
                 for (int it = 0; it < NB - 1; ++it) issue2(it);
+                if (STAGE && o == a.n_out - 1) fetch_params(b + bstride); // the slot's next parameter set travels while this reverse sweep runs
+            }
             double t_hi = t_final;
             for (int it = 0; it < T; ++it) {
                 const int step = T - 1 - it, bi = it % NB;
@@ -744,13 +782,28 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
     }
 }
 
-template <class Tab, bool ADAPTIVE, bool EXACT>
+// Staging needs room for SLOTS parameter sets next to the step-block buffers, one seed per trajectory, and 16-byte aligned
+// parameter sets (the bulk copy's requirement; cudaMalloc'ed and page-locked buffers are, a caller's sub-array may not be)
+bool stage_ok(int blk_doubles, int sadj, int n_out, const void *params)
+{
+    if (!VA_T8_STAGE || VA_T8_P3 || SLOTS != 4 || n_out > 1) return false;
+    if (const char *env = getenv("VA_T8_NO_STAGE"))
+        if (atoi(env) != 0) return false;
+    if (reinterpret_cast<uintptr_t>(params) & 15) return false;
+    return (size_t)SLOTS * (NB_STAGED * buf_doubles(blk_doubles, sadj) + PA_DOUBLES) * 8 <= 220 * 1024;
+}
+size_t smem_bytes(int blk_doubles, int sadj, bool stage)
+{
+    return (size_t)SLOTS * ((stage ? NB_STAGED : NB) * buf_doubles(blk_doubles, sadj) + (stage ? PA_DOUBLES : 0)) * 8;
+}
+
+template <class Tab, bool ADAPTIVE, bool EXACT, bool STAGE>
 cudaError_t launch_k(const VaGlvWideArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)SLOTS * NB * buf_doubles(a.blk_doubles, Tab::SADJ) * 8;
-    cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = smem_bytes(a.blk_doubles, Tab::SADJ, STAGE);
+    cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, EXACT, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_glv_t8<Tab, ADAPTIVE, EXACT><<<a.grid, NT, smem, st>>>(a);
+    k_glv_t8<Tab, ADAPTIVE, EXACT, STAGE><<<a.grid, NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -765,20 +818,21 @@ cudaError_t launch(const VaGlvWideArgs &a_in, cudaStream_t st)
         a.coef.b[m] = Tab::b(m);
         a.coef.db[m] = Tab::db(m);
     }
-    return a.n == NP ? launch_k<Tab, ADAPTIVE, true>(a, st) : launch_k<Tab, ADAPTIVE, false>(a, st);
+    const bool stage = stage_ok(a.blk_doubles, Tab::SADJ, a.n_out, a.params);
+    if (a.n == NP) return stage ? launch_k<Tab, ADAPTIVE, true, true>(a, st) : launch_k<Tab, ADAPTIVE, true, false>(a, st);
+    return stage ? launch_k<Tab, ADAPTIVE, false, true>(a, st) : launch_k<Tab, ADAPTIVE, false, false>(a, st);
 }
 
 template <class Tab, bool ADAPTIVE>
-cudaError_t occupancy(int n, size_t smem, int *ctas_per_sm)
+cudaError_t occupancy(int n, size_t smem, bool stage, int *ctas_per_sm)
 {
-    if (n == NP) {
-        cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto occ = [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_t8<Tab, ADAPTIVE, true>, NT, smem);
-    }
-    cudaError_t e = cudaFuncSetAttribute(k_glv_t8<Tab, ADAPTIVE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_glv_t8<Tab, ADAPTIVE, false>, NT, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, NT, smem);
+    };
+    if (n == NP) return stage ? occ(k_glv_t8<Tab, ADAPTIVE, true, true>) : occ(k_glv_t8<Tab, ADAPTIVE, true, false>);
+    return stage ? occ(k_glv_t8<Tab, ADAPTIVE, false, true>) : occ(k_glv_t8<Tab, ADAPTIVE, false, false>);
 }
 
 int sadj_of(int stepper)
@@ -810,12 +864,15 @@ cudaError_t va_glv_t8_config(int n, int stepper, int n_out, int device, int *gri
     int sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess) return err;
-    const size_t smem = (size_t)SLOTS * NB * buf_doubles(va_glv_t8_block_doubles(stepper, n_out), sadj_of(stepper)) * 8;
+    // the staged form is what the launcher picks for one seed per trajectory (an unaligned parameter pointer falls back at launch time
+    // to the form with the smaller shared-memory footprint, so its occupancy is at least this)
+    const bool stage = stage_ok(va_glv_t8_block_doubles(stepper, n_out), sadj_of(stepper), n_out, nullptr);
+    const size_t smem = smem_bytes(va_glv_t8_block_doubles(stepper, n_out), sadj_of(stepper), stage);
     int occ = 0;
     switch (stepper) {
-    case VA_RK_RK4: err = occupancy<TabRK4, false>(n, smem, &occ); break;
-    case VA_RK_CK54: err = occupancy<TabCK54, true>(n, smem, &occ); break;
-    case VA_RK_DOPRI5: err = occupancy<TabDOPRI5, true>(n, smem, &occ); break;
+    case VA_RK_RK4: err = occupancy<TabRK4, false>(n, smem, stage, &occ); break;
+    case VA_RK_CK54: err = occupancy<TabCK54, true>(n, smem, stage, &occ); break;
+    case VA_RK_DOPRI5: err = occupancy<TabDOPRI5, true>(n, smem, stage, &occ); break;
     default: return cudaErrorInvalidValue;
     }
     if (err != cudaSuccess) return err;
