@@ -666,6 +666,45 @@ def test_glv_warp_specialised_kernel_returns_the_same_bits(va, monkeypatch, N, B
     assert_close(r1["mu"][:nb, 0], o["mu"], what="mu vs oracle")
 
 
+@pytest.mark.parametrize("N", [64, 50])
+def test_glv_parameter_staging_and_its_fallbacks_return_the_same_bits(va, monkeypatch, N):
+    """With one seed per trajectory va_glv_t8.cu brings each parameter set into shared memory with one TMA bulk copy and cuts both
+    register tiles from there; the copy needs 16-byte aligned parameter sets, so a caller's device array that starts on an odd
+    multiple of 8 bytes falls back to the per-lane global loads at launch time, as does VA_T8_NO_STAGE=1. The arithmetic is the
+    same: the three paths must return identical bits (several trajectories per slot, padded species count)."""
+    import torch
+    B = 2100
+    npar = N * N + N
+    dev = torch.device("cuda:0")
+    raw = torch.empty(B * npar + 1, dtype=torch.float64, device=dev)
+    p_aligned = raw[:-1].view(B, npar)
+    x0 = torch.empty(B, N, dtype=torch.float64, device=dev)
+    va.synth_batch_device(va.SYS_GLV, N, 77, 0, B, p_aligned, x0)
+    keep = p_aligned.clone()
+    p_odd = raw[1:].view(B, npar)  # same values, 8 bytes further: not 16-byte aligned
+    p_odd.copy_(keep)
+    assert keep.data_ptr() % 16 == 0 and p_odd.data_ptr() % 16 == 8
+    out = []
+    for params, nostage in ((keep, False), (p_odd, False), (keep, True)):
+        if nostage:
+            monkeypatch.setenv("VA_T8_NO_STAGE", "1")
+        xf, lam, mu = (torch.empty(B, N, dtype=torch.float64, device=dev), torch.ones(B, 1, N, dtype=torch.float64, device=dev),
+                       torch.empty(B, 1, npar, dtype=torch.float64, device=dev))
+        musum = torch.empty(1, npar, dtype=torch.float64, device=dev)
+        lam_s = torch.ones(B, 1, N, dtype=torch.float64, device=dev)
+        na = torch.empty(B, dtype=torch.int32, device=dev)
+        with va.Engine(va.SYS_GLV, N, va.RK_CK54, True, 1e-8, 1e-8) as e:
+            assert e.info()["kernel_name"] == "k_glv_t8"
+            e.call("va_forward_adjoint_batch", B, x0, params, 0.0, 10.0, 1e-3, xf, lam, mu, va.OBJ_SEED, va.REDUCE_NONE, na)
+            e.call("va_forward_adjoint_batch", B, x0, params, 0.0, 10.0, 1e-3, xf, lam_s, musum, va.OBJ_SEED, va.REDUCE_SUM)
+            torch.cuda.synchronize()
+        out.append((xf, lam, mu, musum, na))
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert torch.equal(a, b)
+    assert int(out[0][4].min()) > 5 and torch.isfinite(out[0][2]).all()
+
+
 def test_glv64_dead_step_blocks_dropped_from_l2_change_nothing(va, monkeypatch):
     """VA_T8_DISCARD=1: with more trajectories than slots the headline kernel drops the L2 lines of a trajectory's step blocks once its
     gradient accumulation has read them (discard.global.L2; -30 % DRAM traffic, -1.1 % rate, hence opt-in). The blocks are dead by
