@@ -111,7 +111,8 @@ typedef struct va_batch_args {
     double ti, tf, dt0;
     int32_t objective;    /* va_objective                                                                       */
     int32_t reduce;       /* va_reduce                                                                          */
-    int32_t mem;          /* va_mem: where x0/params/x_final/lambda/mu/n_accept/... live                        */
+    int32_t mem;          /* va_mem: where x0/params/x_final/lambda/mu/n_accept/... live. VA_MEM_DEVICE arrays    */
+                          /* of va_forward_adjoint_batch must be 16-byte aligned (VA_E_INVALID otherwise)        */
     int32_t reserved0;
     double *x_final;      /* [B][n_state] out: x(tf)                                                            */
     double *lambda;       /* [B][n_out][n_state] in (VA_OBJ_SEED): dJ/dx(tf); out: dJ/dx(ti)                    */

@@ -667,25 +667,22 @@ def test_glv_warp_specialised_kernel_returns_the_same_bits(va, monkeypatch, N, B
 
 
 @pytest.mark.parametrize("N", [64, 50])
-def test_glv_parameter_staging_and_its_fallbacks_return_the_same_bits(va, monkeypatch, N):
+def test_glv_parameter_staging_returns_the_same_bits_and_misaligned_device_arrays_are_refused(va, monkeypatch, N):
     """With one seed per trajectory va_glv_t8.cu brings each parameter set into shared memory with one TMA bulk copy and cuts both
-    register tiles from there; the copy needs 16-byte aligned parameter sets, so a caller's device array that starts on an odd
-    multiple of 8 bytes falls back to the per-lane global loads at launch time, as does VA_T8_NO_STAGE=1. The arithmetic is the
-    same: the three paths must return identical bits (several trajectories per slot, padded species count)."""
+    register tiles from there; VA_T8_NO_STAGE=1 keeps the per-lane global loads. Same arithmetic: identical bits (several
+    trajectories per slot, padded species count). Both forms -- like every kernel here -- use 16-byte accesses on the caller's
+    device arrays, so the fused call refuses a device array that starts on an odd multiple of 8 bytes with VA_E_INVALID instead
+    of faulting inside the kernel (found by this test: it used to be a sticky 'misaligned address' error)."""
     import torch
     B = 2100
     npar = N * N + N
     dev = torch.device("cuda:0")
     raw = torch.empty(B * npar + 1, dtype=torch.float64, device=dev)
-    p_aligned = raw[:-1].view(B, npar)
+    params = raw[:-1].view(B, npar)
     x0 = torch.empty(B, N, dtype=torch.float64, device=dev)
-    va.synth_batch_device(va.SYS_GLV, N, 77, 0, B, p_aligned, x0)
-    keep = p_aligned.clone()
-    p_odd = raw[1:].view(B, npar)  # same values, 8 bytes further: not 16-byte aligned
-    p_odd.copy_(keep)
-    assert keep.data_ptr() % 16 == 0 and p_odd.data_ptr() % 16 == 8
+    va.synth_batch_device(va.SYS_GLV, N, 77, 0, B, params, x0)
     out = []
-    for params, nostage in ((keep, False), (p_odd, False), (keep, True)):
+    for nostage in (False, True):
         if nostage:
             monkeypatch.setenv("VA_T8_NO_STAGE", "1")
         xf, lam, mu = (torch.empty(B, N, dtype=torch.float64, device=dev), torch.ones(B, 1, N, dtype=torch.float64, device=dev),
@@ -698,10 +695,17 @@ def test_glv_parameter_staging_and_its_fallbacks_return_the_same_bits(va, monkey
             e.call("va_forward_adjoint_batch", B, x0, params, 0.0, 10.0, 1e-3, xf, lam, mu, va.OBJ_SEED, va.REDUCE_NONE, na)
             e.call("va_forward_adjoint_batch", B, x0, params, 0.0, 10.0, 1e-3, xf, lam_s, musum, va.OBJ_SEED, va.REDUCE_SUM)
             torch.cuda.synchronize()
+            if not nostage:
+                keep = params.clone()
+                odd = raw[1:].view(B, npar)  # 8 bytes further: not 16-byte aligned
+                odd.copy_(keep)
+                assert odd.data_ptr() % 16 == 8
+                with pytest.raises(va.EngineError, match="16-byte aligned"):
+                    e.call("va_forward_adjoint_batch", B, x0, odd, 0.0, 10.0, 1e-3, xf.clone(), lam.clone(), mu.clone(), va.OBJ_SEED, va.REDUCE_NONE)
+                params = keep
         out.append((xf, lam, mu, musum, na))
-    for other in out[1:]:
-        for a, b in zip(out[0], other):
-            assert torch.equal(a, b)
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
     assert int(out[0][4].min()) > 5 and torch.isfinite(out[0][2]).all()
 
 

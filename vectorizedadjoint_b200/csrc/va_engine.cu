@@ -672,6 +672,15 @@ static int single_get_info(va_engine *e, va_engine_info *info)
 int va_single_forward_adjoint(va_engine *e, const va_batch_args *a)
 {
     if (int rc = check_args(e, a, true)) return rc;
+    if (a->mem == VA_MEM_DEVICE) {
+        // the fused call hands the caller's device arrays to the kernels, which read and write them with 16-byte vector accesses
+        // and bulk copies: a misaligned pointer would be a sticky "misaligned address" fault inside the kernel. (Host arrays, and
+        // the arrays of the split API, are copied into the engine's own buffers: no constraint.)
+        const void *ptrs[] = {a->x0, a->params, a->x_final, a->lambda, a->mu};
+        for (const void *q : ptrs)
+            if (reinterpret_cast<uintptr_t>(q) & 15)
+                return fail(VA_E_INVALID, "device arrays must be 16-byte aligned (cudaMalloc / torch allocations are; pass an aligned copy of a sub-array)");
+    }
     return run_call(e, a, false);
 }
 

@@ -103,6 +103,11 @@ using va_tma::policy_evict_last;
 using va_tma::policy_evict_first;
 using va_tma::mbar_wait;
 using va_tma::fence_proxy_async;
+#if defined(VA_T8_FENCE_ALL) && VA_T8_FENCE_ALL
+__device__ __forceinline__ void fence_proxy_async_global() { va_tma::fence_proxy_async(); } // experiment: the all-spaces form
+#else
+using va_tma::fence_proxy_async_global;
+#endif
 using va_tma::ldg_hint;
 __device__ __forceinline__ void st_hint(double *p, double v, uint64_t policy) { va_tma::st_hint_relaxed(p, v, policy); }
 // A step block is dead once the gradient accumulation has copied it to shared memory, but its L2 lines are dirty: when the next
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
         const int T = nck;
         if (tid == 0 && !a.skip_forward) st_hint(sp - HDR, t, keep); // header of block T carries the final time
         if (own < n && !isfinite(x)) status |= VA_TRAJ_NONFINITE;
-        fence_proxy_async(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
+        fence_proxy_async_global(); // generic-proxy slab writes -> visible to the TMA reads of the reverse sweep
         status = slot_or(status);
         const bool failed = status & (VA_TRAJ_CKPT_OVERFLOW | VA_TRAJ_NO_PROGRESS);
         const double x_tf = x, t_final = t;
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
 
             // ================================ phase 3: gradient accumulation =====================================
             // Abar[i][j] += v_m[i] X_{m-1}[j] over all steps and stages; accumulator tile rows FH(k), columns FG(c)
-            fence_proxy_async(); // the v sections were written through the generic proxy
+            fence_proxy_async_global(); // the v sections were written through the generic proxy
             slot_sync();
 #if VA_T8_P3
             // ---- FP64 tensor instructions. Abar(64 x 64) += V(64 x K) X(K x 64)^T with K = SADJ T (stage, step) pairs. Warp w of the

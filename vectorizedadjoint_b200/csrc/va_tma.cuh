@@ -103,5 +103,8 @@ __device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy)
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the same for GLOBAL memory only (generic-proxy stores to global memory -> later bulk copies that read them): compiles to
+// FENCE.VIEW.ASYNC.G alone, where the all-spaces form above also emits a MEMBAR
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 } // namespace va_tma
