@@ -110,7 +110,7 @@ def cpu_baseline(sample=0):
     cores = os.cpu_count() or 1
     if sample <= 0:
         rate = _calibrate(cores)
-        sample = int(max(8 * cores, min(65536, rate * 15)))  # ~15 s of CPU work
+        sample = int(max(8 * cores, min(65536, rate * 30)))  # 10-30 s of CPU work: the one-second calibration errs low by up to 2.5x
         sample -= sample % cores
     t, kind = cpu_run(sample, cores)
     out = dict(value=sample / t, unit="gradients/s", cores=cores, kind=kind,

@@ -517,6 +517,19 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
                 continue;
             }
             const uint64_t drop = policy_evict_first(); // last read of this parameter set by this seed
+            // stream the step blocks back, newest first: iteration it <-> step T-1-it, buffer it % NB, NB-1 blocks ahead. The first
+            // requests go out BEFORE the tile is cut, so that they travel meanwhile: every thread is past its reads of the buffers --
+            // the barrier inside slot_or (first seed; the previous trajectory ended behind one as well), or the one here
+            auto issue2 = [&](int it) {
+                if (it < T) {
+                    const int bi = it % NB;
+                    mbar_expect_tx(&mbar[bi], xg_bytes);
+                    bulk_g2s(xg + bi * bstr, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi], keep);
+                }
+            };
+            if (o > 0) slot_sync(); // the gradient accumulation of the previous seed read the buffers
+            if (tid == 0)
+                for (int it = 0; it < NB - 1; ++it) issue2(it);
             // transposed tile: M[k][c] = A[FG(c)][RT hi + (k ^ g)]; the owned component stays `own`. A is re-read (L2 hit),
             // once per seed: the tile must not stay live across phase 3, whose accumulator needs its registers.
 #pragma unroll
@@ -540,18 +553,9 @@ __global__ void __launch_bounds__(NT, MINB) k_glv_t8(const __grid_constant__ VaG
             else lam = (own < n) ? lam_io[own < n ? own : 0] : 0.0;
             double rbar = 0.0;
 
-            // stream the step blocks back, newest first: iteration it <-> step T-1-it, buffer it % NB, NB-1 blocks ahead
-            auto issue2 = [&](int it) {
-                if (it < T) {
-                    const int bi = it % NB;
-                    mbar_expect_tx(&mbar[bi], xg_bytes);
-                    bulk_g2s(xg + bi * bstr, slab + (int64_t)(T - 1 - it) * blk, xg_bytes, &mbar[bi], keep);
-                }
-            };
-            slot_sync(); // every thread is past its reads of the buffers (previous seed / trajectory) -- and of the staged parameters
-            if (tid == 0) {
-                for (int it = 0; it < NB - 1; ++it) issue2(it);
-                if (STAGE && o == a.n_out - 1) fetch_params(b + bstride); // the slot's next parameter set travels while this reverse sweep runs
+            if (STAGE) {
+                slot_sync(); // every thread has cut its tile from the staged parameter set
+                if (tid == 0 && o == a.n_out - 1) fetch_params(b + bstride); // the slot's next one travels while this reverse sweep runs
             }
             double t_hi = t_final;
             for (int it = 0; it < T; ++it) {
