@@ -716,8 +716,10 @@ def main():
             "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
             "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": alg_bytes, "gpm": gpm_vals,
             "peak_source": "DFMA microbenchmark run live on this GPU (va_measure_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
-            "kernel": "k_glv_t8<TabCK54,adaptive,exact> (va_glv_t8.cu; one launch per step per GPU, %d CTAs x %d threads, 64 threads per "
-                      "trajectory; + one row-reduction kernel over the per-slot partial sums)" % (info["sm_count"] * info["ctas_per_sm"], info["threads_per_cta"]),
+            "kernel": "%s<TabCK54,adaptive,exact%s> (one launch per step per GPU, %d CTAs x %d threads, 64 threads per "
+                      "trajectory; + one row-reduction kernel over the per-slot partial sums)" % (
+                          info["kernel_name"], "" if info["kernel_name"] != "k_glv_t8" or os.environ.get("VA_T8_NO_STAGE", "0") not in ("", "0")
+                          else ",parameters staged in shared memory by TMA", info["sm_count"] * info["ctas_per_sm"], info["threads_per_cta"]),
             "kernel_ms": kernel_ms, "flops_per_launch": flops_exec, "flops_counting": "executed algorithmic FP64 flops of rank 0: "
             "(6T+5R)(2N^2+2N) forward + 6T(4N^2+3N) reverse, store-stages policy (no stage recompute)",
             "achieved_reference_policy_formula": flops_refpolicy / (kernel_ms * 1e-3) / 1e12,
